@@ -1,0 +1,189 @@
+/*
+ * sprb200.h -- C ABI of libsprb200.so: the B200 (sm_100a) replacement for the data-parallel hot
+ * path of SPRFittingPaper2023.jl: run_spr_sim! (the ensemble of spatial stochastic particle
+ * simulations) swept over the (kon, koff, konb, reach) grid that builds the surrogate.
+ *
+ * Every entry point is plain C: POD structs, raw pointers and sizes, integer error codes.  No
+ * C++/torch types cross the boundary, nothing throws, no pointer is retained after a call returns.
+ * All paths below are relative to the reference tree (/root/reference).
+ *
+ * Reference interface replaced                               | entry point here
+ * -----------------------------------------------------------+------------------------------------
+ * run_spr_sim!(outputter, biopars, simpars, terminator)      | sprb200_simulate (reduced moments)
+ *   src/forward_simulator.jl:105-366                         | sprb200_simulate_raw (copynumbers)
+ * TotalBoundOutputter / TotalAOutputter accumulation         | SprOut.sum / sumsq / n_used
+ *   src/callbacks.jl:23-33, 105-114; means/vars/sems :54-80  |   (x = B+C or A, integer moments)
+ * SimNumberTerminator / VarianceTerminator                   | SprRun.term_kind, nsims, ssetol,
+ *   src/callbacks.jl:152-223                                 |   minsims, maxsims
+ * setup_spr_sim! (neighbour tables) :37-89                   | sprb200_neighbor_pairs (test hook)
+ * build_surrogate_slice(meta, idxstart, idxend)              | sprb200_build_slice
+ *   src/surrogate.jl:273-300                                 |
+ * build_surrogate_serial(size, surpars, simpars)             | sprb200_build_table
+ *   src/surrogate.jl:203-242                                 |
+ * merge_surrogate_slices (column scatter) :302-318           | sprb200_merge_slice
+ * SimParams(...) L from antigen concentration                | sprb200_domain_length
+ *   src/parameters.jl:124-150, src/utils.jl:10               |
+ * (none: the reference is single-process)                    | sprb200_build_slice_device,
+ *                                                            | sprb200_scatter_table_device:
+ *                                                            | device-resident slabs for the
+ *                                                            | one-rank-per-GPU NCCL gather
+ */
+#ifndef SPRB200_H
+#define SPRB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPRB200_ABI_VERSION 1
+
+/* error codes (all negative); 0 = success */
+enum {
+    SPRB200_OK = 0,
+    SPRB200_ERR_BAD_ARG = -1,      /* NULL/invalid argument, unsorted tsave, N out of range ... */
+    SPRB200_ERR_NO_DEVICE = -2,    /* no CUDA device / not an sm_100 part / bad ordinal */
+    SPRB200_ERR_CUDA = -3,         /* CUDA runtime error, text in sprb200_last_error */
+    SPRB200_ERR_TOO_LARGE = -4,    /* per-trajectory state does not fit in shared memory */
+    SPRB200_ERR_ALLOC = -5,        /* host or device allocation failed */
+    SPRB200_ERR_INTERNAL = -6
+};
+
+typedef struct sprb200_ctx *sprb200_handle;
+
+/* One parameter point.  kon enters the dynamics only as kon*antibodyconcen
+ * (forward_simulator.jl:132); CP only scales the outputter value (callbacks.jl:28) and is applied
+ * by the caller; antigenconcen acts only through SprSim.L. */
+typedef struct {
+    double kon_eff; /* kon * antibodyconcen, s^-1 */
+    double koff;    /* s^-1 */
+    double konb;    /* s^-1 */
+    double reach;   /* nm */
+} SprPoint;
+
+/* Mirror of SimParams (parameters.jl:92-109). */
+typedef struct {
+    int32_t N;                 /* particles, 1..65535 */
+    int32_t DIM;               /* 2 or 3 */
+    double L;                  /* periodic box edge */
+    double tstop;
+    double tstop_AtoB;         /* may be +Inf */
+    int32_t T;                 /* number of save times */
+    const double *tsave;       /* host, T ascending values */
+    int32_t resample_initlocs; /* !=0: fresh uniform positions every replicate (:42-47,138-142) */
+    const double *initlocs;    /* host, N*DIM doubles, DIM contiguous per particle (memory of
+                                  Vector{SVector{DIM,Float64}}); required iff !resample_initlocs */
+} SprSim;
+
+enum { SPRB200_TERM_FIXED = 0, SPRB200_TERM_VARIANCE = 1 };
+enum { SPRB200_OBS_TOTAL_BOUND = 0, SPRB200_OBS_TOTAL_A = 1 };
+
+typedef struct {
+    int32_t term_kind;         /* FIXED: exactly nsims replicates (SimNumberTerminator);
+                                  VARIANCE: VarianceTerminator(ssetol, minsims, maxsims) with the
+                                  reference's sequential stopping rule (callbacks.jl:204-217) */
+    int32_t nsims;
+    double ssetol;
+    int32_t minsims;
+    int32_t maxsims;
+    int32_t observable;        /* SPRB200_OBS_*: x = B+C (callbacks.jl:28) or x = A (:111) */
+    int32_t reserved;
+    uint64_t seed;             /* Philox key */
+    uint64_t param_index_base; /* RNG parameter index of pts[0]; point k uses base+k.  Streams are
+                                  keyed by (seed, parameter index, replicate): results do not depend
+                                  on batching, GPU count or scheduling. */
+} SprRun;
+
+/* Reduced per-point output; every pointer is a caller-allocated HOST buffer or NULL (skipped). */
+typedef struct {
+    int64_t *sum;       /* [npts][T]  sum over used replicates of x */
+    uint64_t *sumsq;    /* [npts][T]  sum of x^2 */
+    int32_t *n_used;    /* [npts]     replicates entering the sums (the terminator's nobs) */
+    uint64_t *n_events; /* [npts]     SSA events simulated for the point (all replicates run) */
+    double *mean;       /* [npts][T]  sum / (n_used * N): the reference's means(o) for CP = 1 */
+} SprOut;
+
+/* Mirror of SurrogateParams ranges + surrogate_size[1:4] (surrogate.jl:9-24, 208-211):
+ * axis k takes n[k] values range(lo[k], hi[k], length=n[k]); axes 0..2 are log10 of
+ * kon*[Ab], koff, konb; axis 3 is reach. */
+typedef struct {
+    double lo[4];
+    double hi[4];
+    int32_t n[4];
+} SprGrid;
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+int sprb200_abi_version(void);
+/* Creates a context on CUDA device `device_ordinal` (its own non-default streams and device
+ * arenas).  One handle per GPU per host thread; a handle is not thread-safe. */
+int sprb200_create(int device_ordinal, sprb200_handle *out);
+void sprb200_destroy(sprb200_handle h);
+/* Text of the last error on this handle (or of the last failed create when h == NULL). */
+const char *sprb200_last_error(sprb200_handle h);
+/* Counters of the last simulate/build call: trajectories run, events simulated, kernel launches,
+ * device milliseconds between the first and last kernel (CUDA events on the handle's stream). */
+int sprb200_last_stats(sprb200_handle h, uint64_t *trajectories, uint64_t *events,
+                       uint64_t *kernel_launches, double *device_ms);
+
+/* ---- helpers --------------------------------------------------------------------------- */
+/* L = (N / agc)^(1/DIM), agc = 6.02214076e-7*antigenconcen if convert_units (parameters.jl:138-139) */
+double sprb200_domain_length(int32_t N, int32_t DIM, double antigenconcen, int32_t convert_units);
+/* value i0 (0-based) of range(lo, hi, length=n) */
+double sprb200_grid_value(double lo, double hi, int32_t n, int32_t i0);
+/* parameter point of 1-based linear index idx (kon fastest ... reach slowest, surrogate.jl:284) */
+int sprb200_grid_point(const SprGrid *grid, int64_t idx, SprPoint *out);
+
+/* ---- forward simulation (run_spr_sim!) -------------------------------------------------- */
+/* Simulates npts parameter points x replicates; blocking; host buffers in, host buffers out. */
+int sprb200_simulate(sprb200_handle h, const SprSim *sim, const SprPoint *pts, int64_t npts,
+                     const SprRun *run, const SprOut *out);
+
+/* Raw copynumbers for arbitrary outputter/terminator replay on the host: FIXED nsims replicates,
+ * B_out/C_out are uint16 [npts][nsims][T] (A = N - B - 2C; rows of copynumbers,
+ * forward_simulator.jl:189-191).  Either pointer may be NULL. */
+int sprb200_simulate_raw(sprb200_handle h, const SprSim *sim, const SprPoint *pts, int64_t npts,
+                         const SprRun *run, uint16_t *B_out, uint16_t *C_out, uint64_t *n_events);
+
+/* Test hook for the neighbour tables: builds the table of one trajectory exactly as the kernel
+ * does (resampled positions of (seed, param_index, replicate) when sim->resample_initlocs, else
+ * sim->initlocs) and returns it in CSR form.  positions_out: N*DIM doubles (lattice positions in
+ * [0,L) in the kernel's sorted numbering) or NULL; off_out: N+1; nbr_out: up to nbr_cap entries.
+ * Returns the number of directed entries (2 x pairs) or a negative error. */
+int64_t sprb200_neighbor_table(sprb200_handle h, const SprSim *sim, double reach, uint64_t seed,
+                               uint64_t param_index, uint32_t replicate, double *positions_out,
+                               int32_t *off_out, int32_t *nbr_out, int64_t nbr_cap);
+
+/* ---- surrogate build -------------------------------------------------------------------- */
+/* build_surrogate_slice: means of 1-based linear indices idxstart..idxend (inclusive), CP = 1,
+ * [Ab] = 1; out_TxNidx is T x nidx column-major (time fastest), i.e. out[n*T + s].
+ * n_used / n_events: [nidx] or NULL.  run->param_index_base is ignored: point idx always uses RNG
+ * parameter index idx-1, so any slicing reproduces the full table bit for bit. */
+int sprb200_build_slice(sprb200_handle h, const SprGrid *grid, const SprSim *sim, const SprRun *run,
+                        int64_t idxstart, int64_t idxend, double *out_TxNidx, int32_t *n_used,
+                        uint64_t *n_events);
+/* build_surrogate_serial: the full "FirstMoment" array (n1,n2,n3,n4,T) column-major (kon fastest,
+ * time slowest), out_table[(s*P) + idx-1], P = n1*n2*n3*n4. */
+int sprb200_build_table(sprb200_handle h, const SprGrid *grid, const SprSim *sim, const SprRun *run,
+                        double *out_table, int32_t *n_used, uint64_t *n_events);
+/* merge_surrogate_slices: scatters a T x nidx slice into the (.., T) table (host, no GPU work). */
+int sprb200_merge_slice(const SprGrid *grid, int32_t T, const double *slice_TxNidx, int64_t idxstart,
+                        int64_t idxend, double *table);
+
+/* ---- device-resident variants (one rank per GPU; NCCL gather done by the caller) ----------- */
+/* Same as sprb200_build_slice for an arbitrary strided index set idx = idxstart + k*stride,
+ * k = 0..count-1 (1-based idx).  d_out_NidxxT is a DEVICE pointer to count*T doubles, row k = mean
+ * curve of index k ([count][T], time fastest); d_n_used (int32[count]) and d_n_events
+ * (uint64[count]) are device pointers or NULL.  Asynchronous work is complete on return. */
+int sprb200_build_slice_device(sprb200_handle h, const SprGrid *grid, const SprSim *sim,
+                               const SprRun *run, int64_t idxstart, int64_t stride, int64_t count,
+                               double *d_out_NidxxT, int32_t *d_n_used, uint64_t *d_n_events);
+/* Device transpose/scatter of gathered slabs into FirstMoment order: for k in 0..count-1,
+ * d_table[s*P + (idxstart-1 + k*stride)] = d_rows[k*T + s]. */
+int sprb200_scatter_table_device(sprb200_handle h, const double *d_rows, int64_t idxstart,
+                                 int64_t stride, int64_t count, int32_t T, int64_t P, double *d_table);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPRB200_H */
