@@ -15,7 +15,7 @@
  *   src/callbacks.jl:23-33, 105-114; means/vars/sems :54-80  |   (x = B+C or A, integer moments)
  * SimNumberTerminator / VarianceTerminator                   | SprRun.term_kind, nsims, ssetol,
  *   src/callbacks.jl:152-223                                 |   minsims, maxsims
- * setup_spr_sim! (neighbour tables) :37-89                   | sprb200_neighbor_pairs (test hook)
+ * setup_spr_sim! (neighbour tables) :37-89                   | sprb200_neighbor_table (test hook)
  * build_surrogate_slice(meta, idxstart, idxend)              | sprb200_build_slice
  *   src/surrogate.jl:273-300                                 |
  * build_surrogate_serial(size, surpars, simpars)             | sprb200_build_table
@@ -88,7 +88,8 @@ typedef struct {
     int32_t minsims;
     int32_t maxsims;
     int32_t observable;        /* SPRB200_OBS_*: x = B+C (callbacks.jl:28) or x = A (:111) */
-    int32_t reserved;
+    int32_t replicate_base;    /* index of the first replicate (RNG counter); 0 unless a caller
+                                  continues an earlier run of the same parameter index */
     uint64_t seed;             /* Philox key */
     uint64_t param_index_base; /* RNG parameter index of pts[0]; point k uses base+k.  Streams are
                                   keyed by (seed, parameter index, replicate): results do not depend
@@ -182,6 +183,20 @@ int sprb200_build_slice_device(sprb200_handle h, const SprGrid *grid, const SprS
  * d_table[s*P + (idxstart-1 + k*stride)] = d_rows[k*T + s]. */
 int sprb200_scatter_table_device(sprb200_handle h, const double *d_rows, int64_t idxstart,
                                  int64_t stride, int64_t count, int32_t T, int64_t P, double *d_table);
+
+/* Arbitrary index sets (block-cyclic sharding over ranks): idx[k] are 1-based linear grid indices in
+ * host memory; row k of the [count][T] output is the mean curve of idx[k]. */
+int sprb200_build_indices_device(sprb200_handle h, const SprGrid *grid, const SprSim *sim,
+                                 const SprRun *run, const int64_t *idx, int64_t count,
+                                 double *d_out_NidxxT, int32_t *d_n_used, uint64_t *d_n_events);
+/* Host-buffer variant of the above (out_NidxxT, n_used, n_events are host pointers; the latter two
+ * may be NULL). */
+int sprb200_build_indices(sprb200_handle h, const SprGrid *grid, const SprSim *sim, const SprRun *run,
+                          const int64_t *idx, int64_t count, double *out_NidxxT, int32_t *n_used,
+                          uint64_t *n_events);
+/* d_table[s*P + idx[k]-1] = d_rows[k*T + s] for a host index list (after the NCCL gather). */
+int sprb200_scatter_rows_device(sprb200_handle h, const double *d_rows, const int64_t *idx,
+                                int64_t count, int32_t T, int64_t P, double *d_table);
 
 #ifdef __cplusplus
 }

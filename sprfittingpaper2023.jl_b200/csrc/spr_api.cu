@@ -64,6 +64,7 @@ struct sprb200_ctx {
     uint64_t st_traj = 0, st_events = 0, st_launches = 0;
     double st_ms = 0.0;
     size_t curve_budget = (size_t)8 << 30;
+    double cap_scale = 1.0;   // SPRB200_CAP_SCALE (test hook): shrinks the a-priori table capacity
 };
 
 namespace {
@@ -109,6 +110,8 @@ int check_run(sprb200_ctx *h, const SprRun *run) {
         if (!(run->ssetol >= 0.0)) return fail(h, SPRB200_ERR_BAD_ARG, "ssetol must be >= 0");
     } else
         return fail(h, SPRB200_ERR_BAD_ARG, "unknown term_kind");
+    if (run->replicate_base < 0 || (long long)run->replicate_base + 1000000 > 0x7fffffffLL)
+        return fail(h, SPRB200_ERR_BAD_ARG, "replicate_base out of range");
     if (run->observable != SPRB200_OBS_TOTAL_BOUND && run->observable != SPRB200_OBS_TOTAL_A)
         return fail(h, SPRB200_ERR_BAD_ARG, "unknown observable");
     return SPRB200_OK;
@@ -126,7 +129,7 @@ int check_points(sprb200_ctx *h, const PointDev *pts, int64_t npts) {
 
 // capacity (directed neighbour entries) that a trajectory at this reach needs with overwhelming
 // probability: mean + 8 sigma of 2 x (pair count); overflowing trajectories are re-run wider.
-int capacity_for(int N, int DIM, double L, double reach) {
+int capacity_for(int N, int DIM, double L, double reach, double cap_scale = 1.0) {
     const double PI = 3.14159265358979323846;
     double frac = DIM == 3 ? (4.0 / 3.0) * PI * reach * reach * reach / (L * L * L) : PI * reach * reach / (L * L);
     if (frac > 1.0) frac = 1.0;
@@ -134,6 +137,7 @@ int capacity_for(int N, int DIM, double L, double reach) {
     double cap = E + 8.0 * std::sqrt(2.0 * E) + 64.0;
     const double maxe = (double)N * (double)(N - 1);
     if (cap > maxe) cap = maxe;
+    cap *= cap_scale;
     long long c = (long long)std::ceil(cap);
     c = (c + 511) / 512 * 512;
     if (c < 1024) c = 1024;
@@ -267,7 +271,8 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
         h_active.resize(nb);
         for (int64_t k = 0; k < nb; ++k) h_active[k] = (int32_t)k;
 
-        int rep_lo = 0;
+        const int rbase = run->replicate_base;
+        int rep_lo = 0;                                  // relative to replicate_base
         int rep_hi = variance ? run->minsims : run->nsims;
         while (!h_active.empty()) {
             // ---- partition the active slots into shared-memory capacity classes
@@ -275,7 +280,7 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
             for (int32_t sl : h_active) {
                 const PointDev &p = pts[b0 + sl];
                 int cap, gid = 0;
-                if (sim->resample_initlocs) cap = capacity_for(N, DIM, sim->L, p.reach);
+                if (sim->resample_initlocs) cap = capacity_for(N, DIM, sim->L, p.reach, h->cap_scale);
                 else {
                     const FixedGraph &g = graphs[p.reach];
                     cap = (int)std::min<long long>(std::max<long long>((g.entries + 63) / 64 * 64, 64), 0x7fffffff);
@@ -327,7 +332,7 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                 a.pts = h->pts.as<PointDev>();
                 a.pidx = h->pidx.as<uint32_t>();
                 a.order = h->order.as<int32_t>() + class_off[ci];
-                a.rep0 = rep_lo; a.nrep = rep_hi - rep_lo; a.repstride = maxrep;
+                a.rep0 = rbase + rep_lo; a.nrep = rep_hi - rep_lo; a.repstride = maxrep; a.rep_rowbase = rbase;
                 a.ntickets = (long long)cw.slots.size() * a.nrep;
                 a.ticket_list = nullptr;
                 a.seed_lo = (uint32_t)(run->seed & 0xffffffffu); a.seed_hi = (uint32_t)(run->seed >> 32);
@@ -472,10 +477,11 @@ void grid_point(const SprGrid *g, int64_t lin0, PointDev *out) {
     out->reach = sprb200_grid_value(g->lo[3], g->hi[3], g->n[3], i4);
 }
 
-// shared implementation of the slice builders: rows [count][T] land in d_rows (device)
-int build_rows(sprb200_handle h, const SprGrid *grid, const SprSim *sim, const SprRun *run, int64_t idxstart,
-               int64_t stride, int64_t count, double *d_rows, int32_t *d_nused, uint64_t *d_nevents,
-               int32_t *h_nused, uint64_t *h_nevents) {
+// shared implementation of the slice builders: rows [count][T] land in d_rows (device);
+// idx1[k] are 1-based linear grid indices (kon fastest ... reach slowest, surrogate.jl:284)
+int build_rows(sprb200_handle h, const SprGrid *grid, const SprSim *sim, const SprRun *run, const int64_t *idx1,
+               int64_t count, double *d_rows, int32_t *d_nused, uint64_t *d_nevents, int32_t *h_nused,
+               uint64_t *h_nevents) {
     if (!h) return SPRB200_ERR_BAD_ARG;
     int rc = check_sim(h, sim);
     if (rc) return rc;
@@ -483,12 +489,12 @@ int build_rows(sprb200_handle h, const SprGrid *grid, const SprSim *sim, const S
     if (rc) return rc;
     int64_t P = 0;
     if (grid_total(grid, &P)) return fail(h, SPRB200_ERR_BAD_ARG, "bad grid");
-    if (count < 1 || stride < 1 || idxstart < 1 || idxstart + (count - 1) * stride > P)
-        return fail(h, SPRB200_ERR_BAD_ARG, "index range outside the grid");
+    if (count < 1 || !idx1) return fail(h, SPRB200_ERR_BAD_ARG, "empty index set");
     std::vector<PointDev> pts((size_t)count);
     std::vector<uint32_t> pidx((size_t)count);
     for (int64_t k = 0; k < count; ++k) {
-        const int64_t lin0 = idxstart - 1 + k * stride;
+        if (idx1[k] < 1 || idx1[k] > P) return fail(h, SPRB200_ERR_BAD_ARG, "index outside the grid");
+        const int64_t lin0 = idx1[k] - 1;
         grid_point(grid, lin0, &pts[k]);
         pidx[k] = (uint32_t)lin0;
     }
@@ -496,6 +502,7 @@ int build_rows(sprb200_handle h, const SprGrid *grid, const SprSim *sim, const S
     if (rc) return rc;
     SprRun r = *run;
     r.observable = SPRB200_OBS_TOTAL_BOUND;
+    r.replicate_base = 0;
     RunPlan plan{sim, &r, OBS_TOTAL_BOUND, false};
     const int T = sim->T, N = sim->N;
     return run_points(h, plan, pts.data(), pidx.data(), count, [&](int64_t b0, int64_t nb, const unsigned long long *nev) -> int {
@@ -509,6 +516,12 @@ int build_rows(sprb200_handle h, const SprGrid *grid, const SprSim *sim, const S
         CUDA_TRY(h, cudaStreamSynchronize(s0));
         return SPRB200_OK;
     });
+}
+
+std::vector<int64_t> strided(int64_t idxstart, int64_t stride, int64_t count) {
+    std::vector<int64_t> v((size_t)std::max<int64_t>(count, 0));
+    for (int64_t k = 0; k < count; ++k) v[k] = idxstart + k * stride;
+    return v;
 }
 
 }  // namespace
@@ -551,6 +564,10 @@ int sprb200_create(int device_ordinal, sprb200_handle *out) {
     if (const char *env = std::getenv("SPRB200_CURVE_BYTES")) {
         const long long v = std::atoll(env);
         if (v > 0) h->curve_budget = (size_t)v;
+    }
+    if (const char *env = std::getenv("SPRB200_CAP_SCALE")) {
+        const double v = std::atof(env);
+        if (v > 0.0 && v <= 1.0) h->cap_scale = v;
     }
     *out = h;
     return SPRB200_OK;
@@ -761,7 +778,8 @@ int sprb200_build_slice(sprb200_handle h, const SprGrid *grid, const SprSim *sim
     const int64_t count = idxend - idxstart + 1;
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, h->table.ensure(sizeof(double) * (size_t)count * sim->T));
-    int rc = build_rows(h, grid, sim, run, idxstart, 1, count, h->table.as<double>(), nullptr, nullptr, n_used, n_events);
+    const std::vector<int64_t> idx = strided(idxstart, 1, count);
+    int rc = build_rows(h, grid, sim, run, idx.data(), count, h->table.as<double>(), nullptr, nullptr, n_used, n_events);
     if (rc) return rc;
     // rows [count][T] are exactly the T x nidx column-major slice (time fastest)
     CUDA_TRY(h, cudaMemcpyAsync(out_TxNidx, h->table.p, sizeof(double) * (size_t)count * sim->T, cudaMemcpyDeviceToHost, h->stream[0]));
@@ -778,7 +796,8 @@ int sprb200_build_table(sprb200_handle h, const SprGrid *grid, const SprSim *sim
     CUDA_TRY(h, cudaSetDevice(h->device));
     const size_t elems = (size_t)P * sim->T;
     CUDA_TRY(h, h->rows.ensure(sizeof(double) * elems));
-    int rc = build_rows(h, grid, sim, run, 1, 1, P, h->rows.as<double>(), nullptr, nullptr, n_used, n_events);
+    const std::vector<int64_t> idx = strided(1, 1, P);
+    int rc = build_rows(h, grid, sim, run, idx.data(), P, h->rows.as<double>(), nullptr, nullptr, n_used, n_events);
     if (rc) return rc;
     CUDA_TRY(h, h->table.ensure(sizeof(double) * elems));
     CUDA_TRY(h, launch_scatter(h->rows.as<double>(), 0, 1, P, sim->T, P, h->table.as<double>(), h->stream[0]));
@@ -805,7 +824,44 @@ int sprb200_build_slice_device(sprb200_handle h, const SprGrid *grid, const SprS
                                uint64_t *d_n_events) {
     if (!h) return SPRB200_ERR_BAD_ARG;
     if (!d_out_NidxxT) return fail(h, SPRB200_ERR_BAD_ARG, "d_out is NULL");
-    return build_rows(h, grid, sim, run, idxstart, stride, count, d_out_NidxxT, d_n_used, d_n_events, nullptr, nullptr);
+    if (count < 1 || stride < 1) return fail(h, SPRB200_ERR_BAD_ARG, "bad index range");
+    const std::vector<int64_t> idx = strided(idxstart, stride, count);
+    return build_rows(h, grid, sim, run, idx.data(), count, d_out_NidxxT, d_n_used, d_n_events, nullptr, nullptr);
+}
+
+int sprb200_build_indices_device(sprb200_handle h, const SprGrid *grid, const SprSim *sim, const SprRun *run,
+                                 const int64_t *idx, int64_t count, double *d_out_NidxxT, int32_t *d_n_used,
+                                 uint64_t *d_n_events) {
+    if (!h) return SPRB200_ERR_BAD_ARG;
+    if (!d_out_NidxxT) return fail(h, SPRB200_ERR_BAD_ARG, "d_out is NULL");
+    return build_rows(h, grid, sim, run, idx, count, d_out_NidxxT, d_n_used, d_n_events, nullptr, nullptr);
+}
+
+int sprb200_build_indices(sprb200_handle h, const SprGrid *grid, const SprSim *sim, const SprRun *run,
+                          const int64_t *idx, int64_t count, double *out_NidxxT, int32_t *n_used, uint64_t *n_events) {
+    if (!h) return SPRB200_ERR_BAD_ARG;
+    if (!out_NidxxT || count < 1 || !sim || sim->T < 1) return fail(h, SPRB200_ERR_BAD_ARG, "bad arguments");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, h->table.ensure(sizeof(double) * (size_t)count * sim->T));
+    int rc = build_rows(h, grid, sim, run, idx, count, h->table.as<double>(), nullptr, nullptr, n_used, n_events);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(out_NidxxT, h->table.p, sizeof(double) * (size_t)count * sim->T, cudaMemcpyDeviceToHost, h->stream[0]));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream[0]));
+    return SPRB200_OK;
+}
+
+int sprb200_scatter_rows_device(sprb200_handle h, const double *d_rows, const int64_t *idx, int64_t count, int32_t T,
+                                int64_t P, double *d_table) {
+    if (!h) return SPRB200_ERR_BAD_ARG;
+    if (!d_rows || !d_table || !idx || count < 1 || T < 1) return fail(h, SPRB200_ERR_BAD_ARG, "bad scatter arguments");
+    for (int64_t k = 0; k < count; ++k)
+        if (idx[k] < 1 || idx[k] > P) return fail(h, SPRB200_ERR_BAD_ARG, "index outside the table");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, h->misc.ensure(sizeof(int64_t) * (size_t)count));
+    CUDA_TRY(h, cudaMemcpyAsync(h->misc.p, idx, sizeof(int64_t) * (size_t)count, cudaMemcpyHostToDevice, h->stream[0]));
+    CUDA_TRY(h, launch_scatter_idx(d_rows, h->misc.as<long long>(), count, T, P, d_table, h->stream[0]));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream[0]));
+    return SPRB200_OK;
 }
 
 int sprb200_scatter_table_device(sprb200_handle h, const double *d_rows, int64_t idxstart, int64_t stride, int64_t count,

@@ -323,8 +323,9 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
         double tp = tsave[0];
         uint32_t ndraw = 0;
         unsigned long long nev = 0;
-        uint16_t *crow = a.curve + ((size_t)slot * a.repstride + rep) * (size_t)T;
-        uint16_t *crow2 = a.curve2 ? a.curve2 + ((size_t)slot * a.repstride + rep) * (size_t)T : nullptr;
+        const size_t row = (size_t)slot * a.repstride + (size_t)(rep - a.rep_rowbase);
+        uint16_t *crow = a.curve + row * (size_t)T;
+        uint16_t *crow2 = a.curve2 ? a.curve2 + row * (size_t)T : nullptr;
         const int obs = a.observable;
 
         for (;;) {
@@ -726,6 +727,24 @@ __global__ void scatter_kernel(const double *__restrict__ rows, long long idx0, 
     }
 }
 
+__global__ void scatter_idx_kernel(const double *__restrict__ rows, const long long *__restrict__ idx1, long long count,
+                                   int T, long long P, double *__restrict__ table) {
+    __shared__ double tile[32][33];
+    const long long k0 = (long long)blockIdx.x * 32;
+    const int s0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const long long k = k0 + r;
+        const int s = s0 + threadIdx.x;
+        if (k < count && s < T) tile[r][threadIdx.x] = rows[(size_t)k * T + s];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int s = s0 + r;
+        const long long k = k0 + threadIdx.x;
+        if (k < count && s < T) table[(size_t)s * P + (size_t)(idx1[k] - 1)] = tile[threadIdx.x][r];
+    }
+}
+
 template <int DIM, typename OffT>
 cudaError_t set_smem_attr(int bytes) {
     static int configured = -1;
@@ -873,6 +892,15 @@ cudaError_t launch_scatter(const double *rows, long long idx0, long long stride,
     dim3 grid((unsigned)((count + 31) / 32), (unsigned)((T + 31) / 32));
     dim3 block(32, 8);
     scatter_kernel<<<grid, block, 0, st>>>(rows, idx0, stride, count, T, P, table);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_idx(const double *rows, const long long *idx1, long long count, int T, long long P,
+                               double *table, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((count + 31) / 32), (unsigned)((T + 31) / 32));
+    dim3 block(32, 8);
+    scatter_idx_kernel<<<grid, block, 0, st>>>(rows, idx1, count, T, P, table);
     return cudaGetLastError();
 }
 

@@ -40,6 +40,7 @@ struct TrajArgs {
     long long ntickets;             // norder * nrep (or length of ticket_list)
     const long long *ticket_list;   // optional explicit tickets (re-run after capacity overflow)
     int rep0, nrep, repstride;      // replicates rep0 .. rep0+nrep-1; curve row stride per slot
+    int rep_rowbase;                // curve row of replicate r is r - rep_rowbase
     uint32_t seed_lo, seed_hi;
     unsigned long long *ticket_ctr; // global work counter
     uint16_t *curve;                // [nslots][repstride][T]
@@ -82,4 +83,7 @@ cudaError_t launch_means(const long long *sum, const int32_t *nused, int nslots,
                          double *rows, cudaStream_t st);
 cudaError_t launch_scatter(const double *rows, long long idx0, long long stride, long long count,
                            int T, long long P, double *table, cudaStream_t st);
+// rows [count][T] -> table[s*P + idx1[k]-1] for an explicit (1-based) index list
+cudaError_t launch_scatter_idx(const double *rows, const long long *idx1, long long count, int T, long long P,
+                               double *table, cudaStream_t st);
 }  // namespace spr

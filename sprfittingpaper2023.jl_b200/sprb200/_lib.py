@@ -19,6 +19,7 @@ EXPORTS = [
     "sprb200_domain_length", "sprb200_grid_value", "sprb200_grid_point", "sprb200_simulate",
     "sprb200_simulate_raw", "sprb200_neighbor_table", "sprb200_build_slice", "sprb200_build_table",
     "sprb200_merge_slice", "sprb200_build_slice_device", "sprb200_scatter_table_device",
+    "sprb200_build_indices_device", "sprb200_build_indices", "sprb200_scatter_rows_device",
 ]
 
 
@@ -35,7 +36,7 @@ class SprSim(C.Structure):
 class SprRun(C.Structure):
     _fields_ = [("term_kind", C.c_int32), ("nsims", C.c_int32), ("ssetol", C.c_double),
                 ("minsims", C.c_int32), ("maxsims", C.c_int32), ("observable", C.c_int32),
-                ("reserved", C.c_int32), ("seed", C.c_uint64), ("param_index_base", C.c_uint64)]
+                ("replicate_base", C.c_int32), ("seed", C.c_uint64), ("param_index_base", C.c_uint64)]
 
 
 class SprOut(C.Structure):
@@ -101,6 +102,12 @@ def load():
     L.sprb200_build_slice_device.argtypes = [vp, P(SprGrid), P(SprSim), P(SprRun), i64, i64, i64, vp, vp, vp]
     L.sprb200_scatter_table_device.restype = C.c_int
     L.sprb200_scatter_table_device.argtypes = [vp, vp, i64, i64, i64, i32, i64, vp]
+    L.sprb200_build_indices_device.restype = C.c_int
+    L.sprb200_build_indices_device.argtypes = [vp, P(SprGrid), P(SprSim), P(SprRun), P(i64), i64, vp, vp, vp]
+    L.sprb200_build_indices.restype = C.c_int
+    L.sprb200_build_indices.argtypes = [vp, P(SprGrid), P(SprSim), P(SprRun), P(i64), i64, P(dbl), P(i32), P(u64)]
+    L.sprb200_scatter_rows_device.restype = C.c_int
+    L.sprb200_scatter_rows_device.argtypes = [vp, vp, P(i64), i64, i32, i64, vp]
     if L.sprb200_abi_version() != ABI_VERSION:
         raise ImportError("libsprb200.so ABI version mismatch")
     _lib = L
@@ -125,12 +132,12 @@ class SimSpec:
         self.N, self.DIM, self.T = int(N), int(DIM), len(self.tsave)
 
 
-def make_run(nsims=1000, variance=None, observable=OBS_TOTAL_BOUND, seed=0, param_index_base=0):
+def make_run(nsims=1000, variance=None, observable=OBS_TOTAL_BOUND, seed=0, param_index_base=0, replicate_base=0):
     """variance = (ssetol, minsims, maxsims) selects the VarianceTerminator rule."""
     if variance is None:
-        return SprRun(TERM_FIXED, int(nsims), 0.0, 0, 0, observable, 0, seed, param_index_base)
+        return SprRun(TERM_FIXED, int(nsims), 0.0, 0, 0, observable, int(replicate_base), seed, param_index_base)
     tol, mn, mx = variance
-    return SprRun(TERM_VARIANCE, 0, float(tol), int(mn), int(mx), observable, 0, seed, param_index_base)
+    return SprRun(TERM_VARIANCE, 0, float(tol), int(mn), int(mx), observable, int(replicate_base), seed, param_index_base)
 
 
 def make_grid(logkon_range, logkoff_range, logkonb_range, reach_range, size4):
@@ -239,6 +246,27 @@ class Engine:
         self._check(self.lib.sprb200_build_slice_device(self.h, C.byref(grid), C.byref(sim.c), C.byref(run),
                                                         idxstart, stride, count, C.c_void_p(d_out),
                                                         C.c_void_p(d_n_used or None), C.c_void_p(d_n_events or None)))
+
+    def build_indices_device(self, grid, sim, run, idx, d_out, d_n_used=0, d_n_events=0):
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        self._check(self.lib.sprb200_build_indices_device(self.h, C.byref(grid), C.byref(sim.c), C.byref(run),
+                                                          _ptr(idx, C.c_int64), len(idx), C.c_void_p(d_out),
+                                                          C.c_void_p(d_n_used or None), C.c_void_p(d_n_events or None)))
+
+    def build_indices(self, grid, sim, run, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        out = np.zeros((len(idx), sim.T))
+        nu = np.zeros(len(idx), dtype=np.int32)
+        nev = np.zeros(len(idx), dtype=np.uint64)
+        self._check(self.lib.sprb200_build_indices(self.h, C.byref(grid), C.byref(sim.c), C.byref(run),
+                                                   _ptr(idx, C.c_int64), len(idx), _ptr(out, C.c_double),
+                                                   _ptr(nu, C.c_int32), _ptr(nev, C.c_uint64)))
+        return out, nu, nev
+
+    def scatter_rows_device(self, d_rows, idx, T, P, d_table):
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        self._check(self.lib.sprb200_scatter_rows_device(self.h, C.c_void_p(d_rows), _ptr(idx, C.c_int64), len(idx),
+                                                         T, P, C.c_void_p(d_table)))
 
     def scatter_table_device(self, d_rows, idxstart, stride, count, T, P, d_table):
         self._check(self.lib.sprb200_scatter_table_device(self.h, C.c_void_p(d_rows), idxstart, stride, count, T, P,

@@ -1,0 +1,503 @@
+"""Host-side mirror of the reference's interface for the hot path, on top of the C ABI.
+
+Same names, argument meaning and error behaviour as the Julia package (paths under
+/root/reference); Julia's `f!` becomes `f` here:
+
+  BioPhysParams, biopars_from_fitting_vec      src/parameters.jl:15-50
+  SimParams, getdim, getantigenconcen          src/parameters.jl:92-160
+  muM_to_inv_cubic_nm, inv_cubic_nm_to_muM     src/utils.jl:10-11
+  TotalBoundOutputter, TotalAOutputter,
+  means, means_, vars_, sems                   src/callbacks.jl:12-137
+  SimNumberTerminator, VarianceTerminator,
+  isnotdone, update_, reset_                   src/callbacks.jl:152-223
+  run_spr_sim                                  src/forward_simulator.jl:105-366
+  SurrogateParams, Surrogate,
+  save_surrogate_metadata, save_surrogate,
+  save_surrogate_slice, build_surrogate_serial,
+  build_surrogate_slice, merge_surrogate_slices src/surrogate.jl:9-332
+
+Everything that simulates runs on the GPU through libsprb200.so; there is no CPU path here.
+The reference writes JLD (HDF5) files; neither Julia nor HDF5 exist in this image, so the Python
+side stores the same keys in an .npz container (see INTEGRATION.md for the Julia shim that writes
+real .jld files with the reference's own writer).
+"""
+import math
+import os
+import shutil
+
+import numpy as np
+
+from . import _lib
+
+DEFAULT_SIM_ANTIGENCONCEN = 500 / 149 / 26795 * 1000000  # parameters.jl:4
+
+
+def muM_to_inv_cubic_nm(x):
+    return 6.02214076e-7 * x
+
+
+def inv_cubic_nm_to_muM(x):
+    return x / 6.02214076e-7
+
+
+# ------------------------------------------------------------------ seeding
+# The reference never seeds its RNG.  Here every call draws its Philox key from this generator
+# unless a seed is passed explicitly; set_seed makes whole scripts reproducible.
+_seed_rng = np.random.default_rng()
+
+
+def set_seed(seed):
+    global _seed_rng
+    _seed_rng = np.random.default_rng(seed)
+
+
+def _next_seed():
+    return int(_seed_rng.integers(0, 2 ** 63 - 1))
+
+
+_engines = {}
+
+
+def get_engine(device=0):
+    """Process-wide Engine per device (one libsprb200 context per GPU)."""
+    if device not in _engines:
+        _engines[device] = _lib.Engine(device)
+    return _engines[device]
+
+
+# ------------------------------------------------------------------ parameters.jl
+class BioPhysParams:
+    """parameters.jl:15-30 (mutable, keyword constructor)."""
+
+    def __init__(self, kon, koff, konb, reach, CP=1.0, antigenconcen=DEFAULT_SIM_ANTIGENCONCEN, antibodyconcen=1.0):
+        self.kon, self.koff, self.konb, self.reach = kon, koff, konb, reach
+        self.CP, self.antigenconcen, self.antibodyconcen = CP, antigenconcen, antibodyconcen
+
+    def __repr__(self):
+        return ("BioPhysParams\nkon = %r\nkoff = %r\nkonb = %r\nreach = %r\nCP = %r\n[antigen] = %r\n[antibody] = %r"
+                % (self.kon, self.koff, self.konb, self.reach, self.CP, self.antigenconcen, self.antibodyconcen))
+
+
+def biopars_from_fitting_vec(p, antibodyconcen=1.0, antigenconcen=DEFAULT_SIM_ANTIGENCONCEN):
+    """parameters.jl:43-50: p = [log10 kon, log10 koff, log10 konb, reach, log10 CP]."""
+    return BioPhysParams(10 ** p[0], 10 ** p[1], 10 ** p[2], p[3], 10 ** p[4], antigenconcen, antibodyconcen)
+
+
+class SimParams:
+    """parameters.jl:92-150.  Mutable; scripts may change tsave/tstop/L/nsims between calls."""
+
+    def __init__(self, antigenconcen=DEFAULT_SIM_ANTIGENCONCEN, N=1000, tstop=600.0, tstop_AtoB=math.inf, dt=1.0,
+                 tsave=None, L=None, DIM=3, initlocs=None, resample_initlocs=True, nsims=1000,
+                 convert_agc_units=True):
+        agc = muM_to_inv_cubic_nm(antigenconcen) if convert_agc_units else antigenconcen
+        self.N = int(N)
+        self.DIM = int(DIM)
+        self.tstop = float(tstop)
+        self.tstop_AtoB = float(tstop_AtoB)
+        self.L = float((N / agc) ** (1.0 / DIM)) if L is None else float(L)
+        if initlocs is None:
+            # parameters.jl:141: uniform in [-L/2, L/2]^DIM
+            initlocs = self.L * np.random.default_rng(_next_seed()).random((self.N, self.DIM)) - self.L / 2
+        self.initlocs = np.ascontiguousarray(initlocs, dtype=np.float64).reshape(self.N, self.DIM)
+        # parameters.jl:147: collect(range(0.0, tstop, step=dt))
+        self.tsave = (np.arange(0, int(math.floor(tstop / dt + 1e-12)) + 1) * dt) if tsave is None \
+            else np.asarray(tsave, dtype=np.float64)
+        self.resample_initlocs = bool(resample_initlocs)
+        self.nsims = int(nsims)
+
+    def spec(self):
+        return _lib.SimSpec(self.N, self.DIM, self.L, self.tstop, self.tstop_AtoB, self.tsave,
+                            self.resample_initlocs, None if self.resample_initlocs else self.initlocs)
+
+    def __repr__(self):
+        return ("SimParams\nnumber of particles (N) = %d\ntstop = %r\ntstop_AtoB = %r\nnumber of save points = %d\n"
+                "domain length (L) = %r\nresample_initlocs = %r\nnsims = %d"
+                % (self.N, self.tstop, self.tstop_AtoB, len(self.tsave), self.L, self.resample_initlocs, self.nsims))
+
+
+def getdim(simpars):
+    return simpars.DIM
+
+
+def getantigenconcen(simpars):
+    return simpars.N / (simpars.L ** simpars.DIM)
+
+
+# ------------------------------------------------------------------ callbacks.jl: outputters
+class _Moments:
+    """Per-save-time running moments of x (what OnlineStats.Variance / Mean hold), kept as
+    n, sum x, sum x^2 so that batches from the GPU merge exactly."""
+
+    def __init__(self, T):
+        self.n = 0
+        self.s1 = np.zeros(T)
+        self.s2 = np.zeros(T)
+
+    def add_counts(self, scale, n, isum, isumsq):
+        self.n += int(n)
+        self.s1 += scale * isum.astype(np.float64)
+        self.s2 += scale * scale * isumsq.astype(np.float64)
+
+    def mean(self):
+        return self.s1 / self.n if self.n else np.zeros_like(self.s1)
+
+    def var(self):
+        # OnlineStats: value(Variance) = n > 1 ? unbiased variance : 1.0
+        if self.n > 1:
+            return np.maximum(self.s2 - self.s1 * self.s1 / self.n, 0.0) / (self.n - 1)
+        return np.ones_like(self.s1)
+
+
+class TotalBoundOutputter:
+    """callbacks.jl:12-47: x = (CP/N) (B + C) at every save time, mean and variance."""
+    observable = _lib.OBS_TOTAL_BOUND
+
+    def __init__(self, N):
+        self.bindcnt = _Moments(int(N))
+
+    def __call__(self, *args):
+        if len(args) == 0:       # o(): reset (callbacks.jl:42-47)
+            self.bindcnt = _Moments(len(self.bindcnt.s1))
+        elif len(args) == 4:     # o(tsave, copynumbers, biopars, simpars) (callbacks.jl:23-33)
+            _, copynumbers, biopars, simpars = args
+            x = (biopars.CP / simpars.N) * (np.asarray(copynumbers[1], dtype=np.float64) +
+                                            np.asarray(copynumbers[2], dtype=np.float64))
+            self.bindcnt.n += 1
+            self.bindcnt.s1 += x
+            self.bindcnt.s2 += x * x
+        # o(biopars, simpars): finaliser, nothing to do (callbacks.jl:36-38)
+
+
+class TotalAOutputter:
+    """callbacks.jl:91-130: x = (CP/N) A at every save time, mean only."""
+    observable = _lib.OBS_TOTAL_A
+
+    def __init__(self, N):
+        self.bindcnt = _Moments(int(N))
+
+    def __call__(self, *args):
+        if len(args) == 0:
+            self.bindcnt = _Moments(len(self.bindcnt.s1))
+        elif len(args) == 4:
+            _, copynumbers, biopars, simpars = args
+            x = (biopars.CP / simpars.N) * np.asarray(copynumbers[0], dtype=np.float64)
+            self.bindcnt.n += 1
+            self.bindcnt.s1 += x
+            self.bindcnt.s2 += x * x
+
+
+def means(o):
+    return o.bindcnt.mean()
+
+
+def means_(m, o):
+    m[:] = o.bindcnt.mean()
+
+
+def vars_(o):
+    return o.bindcnt.var()
+
+
+def sems(o):
+    return np.sqrt(o.bindcnt.var()) / math.sqrt(o.bindcnt.n)
+
+
+def nobs(o):
+    return o.bindcnt.n
+
+
+# ------------------------------------------------------------------ callbacks.jl: terminators
+class SimNumberTerminator:
+    """callbacks.jl:152-174."""
+
+    def __init__(self, num_completed_sims=0):
+        self.num_completed_sims = num_completed_sims
+
+
+class VarianceTerminator:
+    """callbacks.jl:186-223: stop at the first n >= minsims with SEM <= ssetol*mean in every bin, or maxsims."""
+
+    def __init__(self, ssetol=0.01, notdone=True, minsims=15, maxsims=250):
+        self.ssetol, self.notdone, self.minsims, self.maxsims = ssetol, notdone, minsims, maxsims
+
+
+def isnotdone(t, biopars, simpars):
+    if isinstance(t, SimNumberTerminator):
+        return t.num_completed_sims < simpars.nsims
+    if isinstance(t, VarianceTerminator):
+        return t.notdone
+    return t.isnotdone(biopars, simpars)
+
+
+def update_(t, outputter, biopars, simpars):
+    if isinstance(t, SimNumberTerminator):
+        t.num_completed_sims += 1
+    elif isinstance(t, VarianceTerminator):
+        m = outputter.bindcnt
+        n = m.n
+        if n < t.minsims:
+            t.notdone = True
+        elif n >= t.maxsims:
+            t.notdone = False
+        else:
+            t.notdone = bool(np.any(np.sqrt(m.var()) > t.ssetol * m.mean() * math.sqrt(n)))
+    else:
+        t.update(outputter, biopars, simpars)
+
+
+def reset_(t):
+    if isinstance(t, SimNumberTerminator):
+        t.num_completed_sims = 0
+    elif isinstance(t, VarianceTerminator):
+        t.notdone = True
+    else:
+        t.reset()
+
+
+# ------------------------------------------------------------------ forward_simulator.jl
+def _point(biopars):
+    return [biopars.kon * biopars.antibodyconcen, biopars.koff, biopars.konb, biopars.reach]
+
+
+def run_spr_sim(outputter, biopars, simpars, terminator=None, seed=None, device=0, param_index=0,
+                replay_chunk=64):
+    """run_spr_sim!(outputter, biopars, simpars, terminator = SimNumberTerminator())
+    (forward_simulator.jl:105-366).  Mutates outputter and terminator like the reference.
+
+    Built-in outputters with built-in terminators run fully reduced on the GPU (integer moments,
+    on-device sequential stopping).  Any other callable outputter / terminator object is replayed on
+    the host, replicate by replicate in order, from raw GPU copynumbers (3 x T integer matrices,
+    rows A, B, C)."""
+    terminator = SimNumberTerminator() if terminator is None else terminator
+    eng = get_engine(device)
+    seed = _next_seed() if seed is None else int(seed)
+    spec = simpars.spec()
+    builtin_out = type(outputter) in (TotalBoundOutputter, TotalAOutputter)
+    builtin_term = type(terminator) in (SimNumberTerminator, VarianceTerminator)
+    if builtin_out and len(outputter.bindcnt.s1) != len(simpars.tsave):
+        raise ValueError("outputter length does not match length(simpars.tsave)")
+    fresh = builtin_out and outputter.bindcnt.n == 0
+    if builtin_out and builtin_term and (fresh or isinstance(terminator, SimNumberTerminator)):
+        scale = biopars.CP / simpars.N
+        if isinstance(terminator, SimNumberTerminator):
+            todo = simpars.nsims - terminator.num_completed_sims
+            if todo > 0:
+                run = _lib.make_run(nsims=todo, observable=outputter.observable, seed=seed,
+                                    param_index_base=param_index, replicate_base=terminator.num_completed_sims)
+                out = eng.simulate(spec, [_point(biopars)], run, want=("sum", "sumsq", "n_used"))
+                outputter.bindcnt.add_counts(scale, out["n_used"][0], out["sum"][0], out["sumsq"][0])
+                terminator.num_completed_sims += int(out["n_used"][0])
+        else:
+            if terminator.notdone:
+                run = _lib.make_run(variance=(terminator.ssetol, terminator.minsims, terminator.maxsims),
+                                    observable=outputter.observable, seed=seed, param_index_base=param_index)
+                out = eng.simulate(spec, [_point(biopars)], run, want=("sum", "sumsq", "n_used"))
+                outputter.bindcnt.add_counts(scale, out["n_used"][0], out["sum"][0], out["sumsq"][0])
+                terminator.notdone = False
+        outputter(biopars, simpars)
+        return None
+    # ---- generic replay: raw copynumbers in replicate order
+    done = 0
+    while isnotdone(terminator, biopars, simpars):
+        chunk = replay_chunk
+        if isinstance(terminator, SimNumberTerminator):
+            chunk = min(chunk, simpars.nsims - terminator.num_completed_sims)
+        run = _lib.make_run(nsims=chunk, seed=seed, param_index_base=param_index, replicate_base=done)
+        B, C, _ = eng.simulate_raw(spec, [_point(biopars)], run)
+        for r in range(chunk):
+            if not isnotdone(terminator, biopars, simpars):
+                break
+            b = B[0, r].astype(np.int64)
+            c = C[0, r].astype(np.int64)
+            copynumbers = np.stack([simpars.N - b - 2 * c, b, c])
+            outputter(simpars.tsave, copynumbers, biopars, simpars)
+            update_(terminator, outputter, biopars, simpars)
+        done += chunk
+    outputter(biopars, simpars)
+    return None
+
+
+# ------------------------------------------------------------------ surrogate.jl
+class SurrogateParams:
+    """surrogate.jl:9-24."""
+
+    def __init__(self, logkon_range, logkoff_range, logkonb_range, reach_range,
+                 antigenconcen=DEFAULT_SIM_ANTIGENCONCEN, antibodyconcen=1.0, CP=1.0):
+        self.logkon_range = tuple(map(float, logkon_range))
+        self.logkoff_range = tuple(map(float, logkoff_range))
+        self.logkonb_range = tuple(map(float, logkonb_range))
+        self.reach_range = tuple(map(float, reach_range))
+        self.antigenconcen, self.antibodyconcen, self.CP = antigenconcen, antibodyconcen, CP
+
+
+_SURPAR_FIELDS = ("logkon_range", "logkoff_range", "logkonb_range", "reach_range", "antigenconcen",
+                  "antibodyconcen", "CP")
+
+
+def _grid(surpars, size4):
+    return _lib.make_grid(surpars.logkon_range, surpars.logkoff_range, surpars.logkonb_range, surpars.reach_range,
+                          size4)
+
+
+def _run_from_terminator(terminator, simpars, seed):
+    if terminator is None:
+        terminator = VarianceTerminator()
+    if isinstance(terminator, VarianceTerminator):
+        return _lib.make_run(variance=(terminator.ssetol, terminator.minsims, terminator.maxsims), seed=seed)
+    if isinstance(terminator, SimNumberTerminator):
+        return _lib.make_run(nsims=simpars.nsims, seed=seed)
+    raise TypeError("surrogate builds support SimNumberTerminator and VarianceTerminator")
+
+
+def build_surrogate_serial(surrogate_size, surpars, simpars, terminator=None, seed=None, device=0):
+    """surrogate.jl:203-242: the (nkon, nkoff, nkonb, nreach, ntime) table, returned as a Fortran-ordered
+    numpy array (same memory as Julia's Array{Float64,5})."""
+    surrogate_size = tuple(int(v) for v in surrogate_size)
+    assert surrogate_size[-1] == len(simpars.tsave)    # surrogate.jl:205
+    seed = _next_seed() if seed is None else int(seed)
+    table, _, _ = get_engine(device).build_table(_grid(surpars, surrogate_size[:4]), simpars.spec(),
+                                                 _run_from_terminator(terminator, simpars, seed))
+    return table.reshape(-1).reshape(surrogate_size, order="F")
+
+
+def unpack_metadata(meta):
+    """surrogate.jl:244-255.  Like the reference, rebuilds a *default-geometry* SimParams from
+    tstop, tstop_AtoB and tsave only (N, L, DIM stored in the metadata are ignored)."""
+    size = tuple(int(v) for v in meta["surrogate_size"])
+    surpars = SurrogateParams(meta["logkon_range"], meta["logkoff_range"], meta["logkonb_range"],
+                              meta["reach_range"])
+    simpars = SimParams(tstop=float(meta["tstop"]), tstop_AtoB=float(meta["tstop_AtoB"]),
+                        tsave=np.asarray(meta["tsave"], dtype=np.float64))
+    return size, surpars, simpars
+
+
+def build_surrogate_slice(surmetadata, idxstart, idxend, terminator=None, seed=None, device=0):
+    """surrogate.jl:273-300: ntime x nidx matrix (Fortran order), column n = means of index idxstart+n-1."""
+    size, surpars, simpars = unpack_metadata(surmetadata)
+    seed = int(surmetadata.get("seed", 0)) if seed is None else int(seed)
+    rows, _, _ = get_engine(device).build_slice(_grid(surpars, size[:4]), simpars.spec(),
+                                                _run_from_terminator(terminator, simpars, seed), int(idxstart),
+                                                int(idxend))
+    return rows.T   # [T, nidx] view with time fastest in memory, like the Julia matrix
+
+
+def _metadata_dict(sursize, surpars, simpars):
+    """keys and values written by save_surrogate_metadata (surrogate.jl:112-123)."""
+    d = {"surrogate_size": np.asarray(sursize, dtype=np.int64)}
+    for f in _SURPAR_FIELDS:
+        d[f] = np.asarray(getattr(surpars, f), dtype=np.float64)
+    d["N"] = np.int64(simpars.N)
+    d["tstop"] = np.float64(simpars.tstop)
+    d["tstop_AtoB"] = np.float64(simpars.tstop_AtoB)
+    d["tsave"] = np.asarray(simpars.tsave, dtype=np.float64)
+    d["L"] = np.float64(simpars.L)
+    d["DIM"] = np.int64(simpars.DIM)
+    return d
+
+
+def _npz(filename):
+    return filename if filename.endswith(".npz") else filename + ".npz"
+
+
+def load(filename):
+    with np.load(_npz(filename)) as z:
+        return {k: z[k] for k in z.files}
+
+
+def save_surrogate_metadata(filename, sursize, surpars, simpars, seed=None):
+    d = _metadata_dict(sursize, surpars, simpars)
+    if seed is not None:
+        d["seed"] = np.uint64(seed)
+    np.savez(_npz(filename), **d)
+
+
+def save_surrogate(filename, surrogate_size, surpars, simpars, terminator=None, seed=None, device=0):
+    """surrogate.jl:151-158."""
+    table = build_surrogate_serial(surrogate_size, surpars, simpars, terminator=terminator, seed=seed, device=device)
+    np.savez(_npz(filename), FirstMoment=table, **_metadata_dict(surrogate_size, surpars, simpars))
+
+
+def save_surrogate_slice(filename, surmetadata, idxstart, idxend, terminator=None, seed=None, device=0):
+    """surrogate.jl:170-179."""
+    sl = build_surrogate_slice(surmetadata, idxstart, idxend, terminator=terminator, seed=seed, device=device)
+    np.savez(_npz(filename), surrogate_slice=np.asfortranarray(sl), idxstart=np.int64(idxstart),
+             idxend=np.int64(idxend))
+
+
+def merge_surrogate_slices(surmetafname, slicefilebasename, nfiles, force=False):
+    """surrogate.jl:302-332: scatters the slice columns into the table and writes it into a copy of the
+    metadata file; returns the merged file name."""
+    meta = load(surmetafname)
+    size = tuple(int(v) for v in meta["surrogate_size"])
+    P = int(np.prod(size[:4]))
+    T = size[4]
+    surpars = SurrogateParams(meta["logkon_range"], meta["logkoff_range"], meta["logkonb_range"], meta["reach_range"])
+    grid = _grid(surpars, size[:4])
+    table = np.zeros((T, P))
+    for fidx in range(1, nfiles + 1):
+        d = load(slicefilebasename + "_%d" % fidx)
+        sl = np.asarray(d["surrogate_slice"])            # [T, nidx]
+        _lib.merge_slice(grid, T, np.ascontiguousarray(sl.T), int(d["idxstart"]), int(d["idxend"]), table)
+    merged = _npz(slicefilebasename + "_merged")
+    if os.path.exists(merged) and not force:
+        raise FileExistsError(merged)
+    shutil.copyfile(_npz(surmetafname), merged)
+    meta["FirstMoment"] = table.reshape(-1).reshape(size, order="F")
+    np.savez(merged, **meta)
+    return merged
+
+
+class Surrogate:
+    """surrogate.jl:55-109: the lookup table with 5-D multilinear interpolation
+    (Interpolations.interpolate(FirstMoment, BSpline(Linear())), fractional 1-based indices)."""
+
+    def __init__(self, lut, surpars=None, simpars=None, surrogate_size=None):
+        if isinstance(lut, str):
+            data = load(lut)
+            table = data["FirstMoment"]
+            if surpars is None:
+                if not all(f in data for f in _SURPAR_FIELDS):
+                    raise KeyError("Not all SurrogateParams fields are in the surrogate file.")
+                surpars = SurrogateParams(data["logkon_range"], data["logkoff_range"], data["logkonb_range"],
+                                          data["reach_range"], float(data["antigenconcen"]),
+                                          float(data["antibodyconcen"]), float(data["CP"]))
+            if simpars is None:
+                if not all(f in data for f in ("N", "tstop", "tstop_AtoB", "tsave", "L", "DIM")):
+                    raise KeyError("Not all needed SimParams fields are in the surrogate file.")
+                simpars = SimParams(antigenconcen=surpars.antigenconcen, N=int(data["N"]), tstop=float(data["tstop"]),
+                                    tstop_AtoB=float(data["tstop_AtoB"]), tsave=data["tsave"], L=float(data["L"]),
+                                    DIM=int(data["DIM"]))
+            if surrogate_size is None and "surrogate_size" in data:
+                surrogate_size = tuple(int(v) for v in data["surrogate_size"])
+        else:
+            table = np.asarray(lut)
+        self.table = np.asfortranarray(table)
+        self.surrogate_size = tuple(self.table.shape) if surrogate_size is None else tuple(surrogate_size)
+        self.surpars, self.simpars = surpars, simpars
+
+    def itp(self, q1, q2, q3, q4, s):
+        """multilinear interpolation at fractional 1-based indices; out of range raises IndexError
+        (Interpolations throws BoundsError)."""
+        q = [float(q1), float(q2), float(q3), float(q4), float(s)]
+        lo, w = [], []
+        for k, v in enumerate(q):
+            n = self.table.shape[k]
+            if not (1.0 <= v <= n):
+                raise IndexError("index %r out of range 1..%d on axis %d" % (v, n, k + 1))
+            i = min(int(math.floor(v)), n - 1) if n > 1 else 1
+            lo.append(i - 1)
+            w.append(v - i)
+        acc = 0.0
+        for corner in range(32):
+            wt = 1.0
+            idx = []
+            for k in range(5):
+                bit = (corner >> k) & 1
+                if bit and self.table.shape[k] == 1:
+                    wt = 0.0
+                    break
+                wt *= w[k] if bit else (1.0 - w[k])
+                idx.append(lo[k] + bit)
+            if wt != 0.0:
+                acc += wt * self.table[tuple(idx)]
+        return acc

@@ -1,0 +1,94 @@
+"""CPU: the C-ABI library loads, exports every symbol include/sprb200.h declares, fails loudly without
+a GPU (no CPU fallback), and its device-free helpers match the reference's formulas."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    h = open(os.path.join(ROOT, "include", "sprb200.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return sorted(set(re.findall(r"\b(sprb200_[a-z_0-9]+)\s*\(", h)))
+
+
+def test_header_and_binding_agree(built_lib):
+    from sprb200 import _lib
+    decl = declared_functions()
+    assert len(decl) >= 19
+    assert sorted(_lib.EXPORTS) == decl
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    L = C.CDLL(built_lib)
+    for name in declared_functions():
+        assert hasattr(L, name), name
+    L.sprb200_abi_version.restype = C.c_int
+    assert L.sprb200_abi_version() == 1
+
+
+def test_no_cpu_fallback(built_lib):
+    """without a CUDA device create() must fail with NO_DEVICE and say so"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import sprb200
+    from sprb200 import _lib
+    with pytest.raises(sprb200.SprB200Error) as ei:
+        sprb200.Engine(0)
+    assert ei.value.code == _lib.ERR_NO_DEVICE
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_product_does_not_import_oracle():
+    """the product path never routes through oracle/ (only tests, smoke and bench's CPU legs may)"""
+    pkg = os.path.join(ROOT, "sprfittingpaper2023.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".jl")):
+                src = open(os.path.join(dirpath, f)).read()
+                code = "\n".join(l for l in src.splitlines() if not l.strip().startswith(("#", "//", "*", "/*")))
+                assert "import oracle" not in code and "from oracle" not in code and "spr_ref" not in code \
+                    and "spr_mirror" not in code, os.path.join(dirpath, f)
+
+
+def test_helpers_match_reference_formulas(built_lib):
+    from sprb200 import _lib
+    L = _lib.load()
+    # parameters.jl:4,138-139 + utils.jl:10
+    assert _lib.domain_length() == pytest.approx((1000 / (6.02214076e-7 * (500 / 149 / 26795 * 1e6))) ** (1 / 3), rel=1e-15)
+    assert _lib.domain_length(1000, 2, 0.01, False) == pytest.approx((1000 / 0.01) ** 0.5, rel=1e-15)
+    # range(lo, hi, length=n)
+    vals = [L.sprb200_grid_value(-3.0, 2.0, 10, i) for i in range(10)]
+    assert np.allclose(vals, np.linspace(-3, 2, 10), rtol=0, atol=1e-15) and vals[-1] == 2.0
+    # CartesianIndices order (surrogate.jl:284-288): kon fastest
+    g = _lib.make_grid((-3, 2), (-4, -1), (-3, 1.5), (2, 35), (3, 4, 5, 6))
+    p = _lib.SprPoint()
+    assert L.sprb200_grid_point(C.byref(g), 1, C.byref(p)) == 0
+    assert (p.kon_eff, p.koff, p.konb, p.reach) == (1e-3, 1e-4, 1e-3, 2.0)
+    assert L.sprb200_grid_point(C.byref(g), 2, C.byref(p)) == 0 and p.kon_eff == pytest.approx(10 ** -0.5) and p.koff == 1e-4
+    assert L.sprb200_grid_point(C.byref(g), 3 * 4 * 5 * 6, C.byref(p)) == 0
+    assert (p.kon_eff, p.koff, p.konb, p.reach) == (100.0, 0.1, pytest.approx(10 ** 1.5), 35.0)
+    assert L.sprb200_grid_point(C.byref(g), 0, C.byref(p)) == _lib.ERR_BAD_ARG
+    assert L.sprb200_grid_point(C.byref(g), 361, C.byref(p)) == _lib.ERR_BAD_ARG
+
+
+def test_merge_slice_scatter(built_lib):
+    """merge_surrogate_slices (surrogate.jl:314-316): column n of a slice -> table[idx, :]"""
+    from sprb200 import _lib
+    g = _lib.make_grid((-3, 2), (-4, -1), (-3, 1.5), (2, 35), (2, 3, 2, 2))
+    P, T = 24, 5
+    rng = np.random.default_rng(0)
+    rows = rng.random((P, T))
+    table = np.zeros((T, P))
+    for a, b in ((1, 7), (8, 8), (9, 24)):
+        _lib.merge_slice(g, T, rows[a - 1:b], a, b, table)
+    assert np.array_equal(table, rows.T)
+    fm = table.reshape(-1).reshape((2, 3, 2, 2, T), order="F")     # Julia's (n1,n2,n3,n4,T)
+    assert fm[1, 2, 0, 1, 3] == rows[1 + 2 * 2 + 0 * 6 + 1 * 12, 3]
+    with pytest.raises(_lib.SprB200Error):
+        _lib.merge_slice(g, T, rows[:2], 24, 25, table)

@@ -1,0 +1,157 @@
+"""-m gpu: statistical parity of the CUDA path with the reference, through the C ABI.
+
+North-star criterion: the GPU mean bound curve lies within 3 standard errors of the reference at
+every time bin, >= 10^4 GPU replicates.  "The reference" is, in decreasing order of authority:
+  (1) the reference's own recorded curves (tests/golden/fit_curves_golden.json, 250 replicates),
+  (2) exact answers derived from its formulas (N=2 chain, monovalent closed form),
+  (3) oracle/spr_ref.c, the CPU restatement of its algorithm (independent RNG: a two-sample test).
+z = (m_gpu - m_ref) / sqrt(SE_gpu^2 + SE_ref^2) per bin, seeds fixed so the test is deterministic.
+Tolerance: max|z| < 3 for (3) as the north star states; < 4 for (1) where SE_ref is estimated from
+the GPU variance / 250 and the 586 bins are strongly autocorrelated; mean z^2 < 2 everywhere."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDF = os.path.join(os.path.dirname(__file__), "golden", "fit_curves_golden.json")
+NREP_GPU = 10000
+
+
+def gpu_moments(engine, sim, point, nsims, seed, N, pidx=0, obs=0):
+    import sprb200
+    out = engine.simulate(sim, [point], sprb200.make_run(nsims=nsims, seed=seed, param_index_base=pidx, observable=obs))
+    n = int(out["n_used"][0])
+    mean = out["sum"][0] / n / N
+    var = (out["sumsq"][0].astype(float) - out["sum"][0].astype(float) ** 2 / n) / (n - 1) / N ** 2
+    return mean, var, n, int(out["n_events"][0])
+
+
+def ref_moments(point, N, DIM, L, tstop, toff, tsave, nrep, seed, copies=None):
+    """reference-algorithm oracle, replicates split over `copies` independent streams (one per core)"""
+    from oracle import ref_oracle as R
+    copies = copies or min(os.cpu_count() or 1, 32)
+    per = max(2, -(-nrep // copies))
+    sim = R.make_sim(N=N, DIM=DIM, tstop=tstop, tstop_AtoB=toff, tsave=tsave, L=L, nsims=per)
+    import ctypes as C
+    pts = np.tile(np.asarray(point, dtype=np.float64), (copies, 1))
+    # per-copy mean only comes back from run_points; get variance via the single-point API on each stream
+    means = np.zeros((copies, len(tsave))); vars_ = np.zeros((copies, len(tsave))); ev = 0
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(c):
+        return R.run(*point, sim, seed=seed, stream=1000 + c)
+    with ThreadPoolExecutor(copies) as ex:
+        res = list(ex.map(one, range(copies)))
+    n = per * copies
+    m = np.mean([r["mean"] for r in res], axis=0)
+    # pooled unbiased variance from per-copy mean/variance
+    ss = sum((per - 1) * r["var"] + per * (r["mean"] - m) ** 2 for r in res)
+    v = ss / (n - 1)
+    ev = sum(r["nevents"] for r in res)
+    return m, v, n, ev
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return json.load(open(GOLDF))
+
+
+@pytest.mark.parametrize("j", [0, 1])
+def test_gpu_vs_reference_recorded_curves(engine, gold, j):
+    import sprb200
+    from sprb200 import _lib
+    p = gold["internal_params"]
+    times = np.array(gold["times"])
+    CP = 10 ** p["logCP"]
+    kon = 10 ** (p["logkon"] + np.log10(gold["antibody_nM"][j] / gold["antibody_nM"][0]))
+    sim = sprb200.SimSpec(1000, 3, _lib.domain_length(), times[-1], 150.0, times)
+    mean, var, n, _ = gpu_moments(engine, sim, [kon, 10 ** p["logkoff"], 10 ** p["logkonb"], p["reach"]], NREP_GPU, 1, 1000, j)
+    z = (CP * mean - np.array(gold["sim_mean"][j])) / (CP * np.sqrt(var / n + var / 250))
+    assert np.abs(z).max() < 4.0, np.abs(z).max()
+    assert (z ** 2).mean() < 2.0
+
+
+def test_gpu_two_particle_chain_exact(engine):
+    import sprb200
+    from oracle import exact
+    locs = np.array([[1.0, 1.0, 1.0], [2.0, 1.0, 1.0]])
+    tsave = np.arange(0.0, 61.0, 1.0)
+    sim = sprb200.SimSpec(2, 3, 100.0, 60.0, 30.0, tsave, resample_initlocs=False, initlocs=locs)
+    for obs, col in ((0, 0), (1, 1)):
+        mean, var, n, _ = gpu_moments(engine, sim, [0.05, 0.1, 0.5, 5.0], 200000, 7, 1, obs=obs)
+        ex = exact.two_particle_ctmc(0.05, 0.1, 0.5, 30.0, tsave)[col]
+        z = (mean - ex)[1:] / np.sqrt(var[1:] / n)
+        assert np.abs(z).max() < 4.0, (obs, np.abs(z).max())
+    # far apart: no pair channel, each particle is monovalent
+    far = np.array([[1.0, 1.0, 1.0], [40.0, 1.0, 1.0]])
+    sim = sprb200.SimSpec(2, 3, 100.0, 60.0, 30.0, tsave, resample_initlocs=False, initlocs=far)
+    mean, var, n, _ = gpu_moments(engine, sim, [0.05, 0.1, 0.5, 5.0], 100000, 8, 2)
+    ex = exact.monovalent_total_bound(0.05, 0.1, 1.0, 1.0, 30.0, tsave)
+    z = (mean - ex)[1:] / np.sqrt(var[1:] / n)
+    assert np.abs(z).max() < 4.0
+
+
+def test_gpu_monovalent_limit(engine):
+    """konb = 0 (and separately reach = 0): E[(B+C)/N] = monovalent_total_bound, Var = p(1-p)/N"""
+    import sprb200
+    from sprb200 import _lib
+    from oracle import exact
+    tsave = np.arange(0.0, 601.0, 1.0)
+    sim = sprb200.SimSpec(1000, 3, _lib.domain_length(), 600.0, 150.0, tsave)
+    ex = exact.monovalent_total_bound(0.01, 0.02, 1.0, 1.0, 150.0, tsave)
+    for point in ([0.01, 0.02, 0.0, 30.0], [0.01, 0.02, 5.0, 0.0]):
+        mean, var, n, _ = gpu_moments(engine, sim, point, NREP_GPU, 3, 1000)
+        z = (mean - ex)[1:] / np.sqrt(ex[1:] * (1 - ex[1:]) / 1000 / n)
+        assert np.abs(z).max() < 4.0
+        assert np.allclose(var[50:], ex[50:] * (1 - ex[50:]) / 1000, rtol=0.1)
+
+
+CASES = {
+    # name: (kon', koff, konb, reach, N, DIM, L, tstop, toff, tsave, ref replicates)
+    "C1-golden-25nM": (10 ** -2.8789331867029184, 10 ** -1.3886105070021626, 10 ** -0.107804350729586,
+                       15.292951569975912, 1000, 3, None, 600.0, 150.0, np.arange(0.0, 601.0, 1.0), 1000),
+    "C1-default-reach30-100nM": (4 * 10 ** -2.8789331867029184, 10 ** -1.3886105070021626, 10 ** -0.107804350729586,
+                                 30.0, 1000, 3, None, 600.0, 150.0, np.arange(0.0, 601.0, 1.0), 1000),
+    "C4a-stress-reach50": (1.0, 0.1, 1.0, 50.0, 1000, 3, None, 600.0, 150.0, np.arange(0.0, 601.0, 1.0), 200),
+    "C4b-stress-2x-density": (1.0, 0.1, 1.0, 50.0, 1000, 3, 187.86, 300.0, 150.0, np.arange(0.0, 301.0, 1.0), 100),
+    "2D-surface": (0.05, 0.02, 0.5, 25.0, 600, 2, None, 400.0, 100.0, np.arange(0.0, 401.0, 2.0), 500),
+    "high-rate-corner": (100.0, 1.0, 31.6, 35.0, 1000, 3, None, 60.0, 20.0, np.arange(0.0, 61.0, 0.5), 200),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_gpu_within_3_se_of_reference_algorithm(engine, oracle_libs, name):
+    import sprb200
+    from sprb200 import _lib
+    kon, koff, konb, reach, N, DIM, L, tstop, toff, tsave, nref = CASES[name]
+    L = _lib.domain_length(N, DIM) if L is None else L
+    sim = sprb200.SimSpec(N, DIM, L, tstop, toff, tsave)
+    nrep = NREP_GPU if "stress" not in name and "corner" not in name else 10000
+    gm, gv, gn, gev = gpu_moments(engine, sim, [kon, koff, konb, reach], nrep, 2023, N, 11)
+    rm, rv, rn, rev = ref_moments([kon, koff, konb, reach], N, DIM, L, tstop, toff, tsave, nref, seed=77)
+    se = np.sqrt(gv / gn + rv / rn)
+    ok = se > 0
+    z = (gm - rm)[ok] / se[ok]
+    assert np.all(gm[~ok] == rm[~ok])
+    assert np.abs(z).max() < 3.0, (name, np.abs(z).max())
+    assert (z ** 2).mean() < 2.0
+    # same process => same events per trajectory
+    assert gev / gn == pytest.approx(rev / rn, rel=0.03)
+
+
+def test_gpu_total_A_observable(engine, oracle_libs):
+    """TotalAOutputter (callbacks.jl:111): A = N - B - 2C"""
+    import sprb200
+    from sprb200 import _lib
+    from oracle import ref_oracle as R
+    tsave = np.arange(0.0, 201.0, 2.0)
+    sim = sprb200.SimSpec(500, 3, _lib.domain_length(500, 3), 200.0, 80.0, tsave)
+    gm, gv, gn, _ = gpu_moments(engine, sim, [0.05, 0.03, 0.6, 28.0], 5000, 5, 500, obs=1)
+    rs = R.make_sim(N=500, tstop=200.0, tstop_AtoB=80.0, tsave=tsave, nsims=300)
+    ro = R.run(0.05, 0.03, 0.6, 28.0, rs, seed=1, observable=1)
+    se = np.sqrt(gv / gn + ro["var"] / ro["n"])
+    z = (gm - ro["mean"])[1:] / se[1:]
+    assert gm[0] == 1.0 and np.abs(z).max() < 3.5
