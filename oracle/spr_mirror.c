@@ -76,6 +76,18 @@ double spr_mirror_neg_log_u53(uint64_t k) {
     return fma((double)(53 - e), 0.6931471805599453, -logm);
 }
 
+/* ---------------------------------------------------------------- waiting time E / a0:
+ * correctly rounded float reciprocal + one Newton step in double; plain division outside float range */
+double spr_mirror_event_dt(double E, double a0) {
+    if (a0 < 1e-30 || a0 > 1e30) return E / a0;
+    float af = (float)a0;
+    float rf = 1.0f / af;
+    double r = (double)rf;
+    double y = E * r;
+    double rem = fma(-a0, y, E);
+    return fma(rem, r, y);
+}
+
 /* ---------------------------------------------------------------- cell grid */
 int spr_mirror_cells_per_axis(int N, int DIM, double L, double reach) {
     int cmax = 1;
@@ -95,9 +107,12 @@ int spr_mirror_cells_per_axis(int N, int DIM, double L, double reach) {
     return nc;
 }
 
+#define POS_BITS 21
+#define POS_MASK ((1u << POS_BITS) - 1u)
+
 typedef struct {
     int N, DIM;
-    uint32_t *spos;   /* N*DIM lattice coordinates, sorted numbering */
+    uint32_t *spos;   /* N*DIM lattice coordinates (21 bits per axis), sorted numbering */
     int *off;         /* N+1 */
     int *nbr;
     int nbr_cap, entries;
@@ -106,8 +121,8 @@ typedef struct {
 static int within(const uint32_t *a, const uint32_t *b, int DIM, double scale, double reach2) {
     double acc = 0.0;
     for (int d = 0; d < DIM; d++) {
-        uint32_t df = a[d] - b[d];
-        uint32_t nd = 0u - df;
+        uint32_t df = (a[d] - b[d]) & POS_MASK;
+        uint32_t nd = (0u - df) & POS_MASK;
         uint32_t m = df < nd ? df : nd;
         double dd = (double)m * scale;
         acc = fma(dd, dd, acc);
@@ -130,7 +145,7 @@ static void build_table_resampled(table_t *t, double L, double reach, uint32_t r
     const int nc = spr_mirror_cells_per_axis(N, DIM, L, reach);
     int ncell = 1;
     for (int d = 0; d < DIM; d++) ncell *= nc;
-    const double scale = L * 0x1.0p-32;
+    const double scale = L * 0x1.0p-21;
     const double reach2 = reach * reach;
     uint32_t *raw = (uint32_t *)malloc(sizeof(uint32_t) * N * DIM);
     int *cell = (int *)malloc(sizeof(int) * N);
@@ -139,8 +154,8 @@ static void build_table_resampled(table_t *t, double L, double reach, uint32_t r
         uint32_t r[4];
         philox4x32_10((uint32_t)i, 0u /* positions stream */, rep, pidx, k0, k1, r);
         int c = 0;
-        for (int d = 0; d < DIM; d++) raw[i * DIM + d] = r[d];
-        for (int d = DIM - 1; d >= 0; d--) c = c * nc + (int)(((uint64_t)r[d] * (uint64_t)nc) >> 32);
+        for (int d = 0; d < DIM; d++) raw[i * DIM + d] = r[d] >> (32 - POS_BITS);   /* top 21 bits */
+        for (int d = DIM - 1; d >= 0; d--) c = c * nc + (int)((raw[i * DIM + d] * (uint32_t)nc) >> POS_BITS);
         cell[i] = c;
         cstart[c + 1]++;
     }
@@ -157,7 +172,7 @@ static void build_table_resampled(table_t *t, double L, double reach, uint32_t r
         t->off[i] = t->entries;
         const uint32_t *ki = t->spos + i * DIM;
         int ci[3] = {0, 0, 0};
-        for (int d = 0; d < DIM; d++) ci[d] = (int)(((uint64_t)ki[d] * (uint64_t)nc) >> 32);
+        for (int d = 0; d < DIM; d++) ci[d] = (int)((ki[d] * (uint32_t)nc) >> POS_BITS);
         const int zlo = DIM == 3 ? lo : 0, zhi = DIM == 3 ? hi : 0;
         for (int dz = zlo; dz <= zhi; dz++) {
             int cz = 0;
@@ -231,7 +246,7 @@ int spr_mirror_trajectory(const MirrorSim *sim, double kon_eff, double koff, dou
     if (off_out) for (int i = 0; i <= N; i++) off_out[i] = tb.off[i];
     if (nbr_out) for (int q = 0; q < tb.entries && q < nbr_cap; q++) nbr_out[q] = tb.nbr[q];
     if (pos_out) {
-        const double scale = sim->L * 0x1.0p-32;
+        const double scale = sim->L * 0x1.0p-21;
         for (int q = 0; q < N * DIM; q++)
             pos_out[q] = sim->resample ? (double)tb.spos[q] * scale : sim->initlocs[q];
     }
@@ -271,7 +286,7 @@ int spr_mirror_trajectory(const MirrorSim *sim, double kon_eff, double koff, dou
         const double cB = cA + koff * (double)cntB;
         const double cP = cB + konb * (double)nAB;
         const double a0 = cP + kc * (double)cntC;
-        double tn = a0 > 0.0 ? t + E / a0 : INFINITY;
+        double tn = a0 > 0.0 ? t + spr_mirror_event_dt(E, a0) : INFINITY;
         int switched = 0;
         if (on && tn >= toff) { tn = toff; switched = 1; }
         if (tn > tp) {

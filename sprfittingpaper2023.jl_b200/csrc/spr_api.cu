@@ -737,7 +737,7 @@ int64_t sprb200_neighbor_table(sprb200_handle h, const SprSim *sim, double reach
             CUDA_TRY(h, cudaMemcpyAsync(h->pidx.p, &pi, sizeof(pi), cudaMemcpyHostToDevice, s0));
             CUDA_TRY(h, h->goff.ensure(sizeof(uint32_t) * (N + 1)));
             CUDA_TRY(h, h->gnbr.ensure(sizeof(uint16_t) * (size_t)lay.cap));
-            CUDA_TRY(h, h->locs.ensure(sizeof(uint32_t) * N * DIM + sizeof(double) * N * DIM));
+            CUDA_TRY(h, h->locs.ensure(sizeof(uint64_t) * N + sizeof(double) * N * DIM));
             CUDA_TRY(h, h->misc.ensure(64));
             TrajArgs a{};
             a.N = N; a.T = sim->T; a.L = sim->L;
@@ -745,7 +745,7 @@ int64_t sprb200_neighbor_table(sprb200_handle h, const SprSim *sim, double reach
             a.seed_lo = (uint32_t)(seed & 0xffffffffu); a.seed_hi = (uint32_t)(seed >> 32);
             a.lay = lay;
             CUDA_TRY(h, launch_table_dump(a, DIM, replicate, 0, h->goff.as<uint32_t>(), h->gnbr.as<uint16_t>(),
-                                          h->locs.as<uint32_t>(), h->misc.as<long long>(), s0));
+                                          h->locs.as<uint64_t>(), h->misc.as<long long>(), s0));
             CUDA_TRY(h, cudaMemcpyAsync(&total, h->misc.p, 8, cudaMemcpyDeviceToHost, s0));
             CUDA_TRY(h, cudaStreamSynchronize(s0));
             if (total >= 0) break;
@@ -754,14 +754,16 @@ int64_t sprb200_neighbor_table(sprb200_handle h, const SprSim *sim, double reach
             cap = (int)std::min<long long>(maxe + 64, (long long)cap + cap / 4 + 512);
         }
         nbr.resize((size_t)std::max<long long>(total, 1));
-        std::vector<uint32_t> spos((size_t)N * DIM);
+        std::vector<uint64_t> spos((size_t)N);
         CUDA_TRY(h, cudaMemcpyAsync(off.data(), h->goff.p, sizeof(uint32_t) * (N + 1), cudaMemcpyDeviceToHost, s0));
         CUDA_TRY(h, cudaMemcpyAsync(nbr.data(), h->gnbr.p, sizeof(uint16_t) * total, cudaMemcpyDeviceToHost, s0));
-        CUDA_TRY(h, cudaMemcpyAsync(spos.data(), h->locs.p, sizeof(uint32_t) * N * DIM, cudaMemcpyDeviceToHost, s0));
+        CUDA_TRY(h, cudaMemcpyAsync(spos.data(), h->locs.p, sizeof(uint64_t) * N, cudaMemcpyDeviceToHost, s0));
         CUDA_TRY(h, cudaStreamSynchronize(s0));
         if (positions_out) {
-            const double scale = sim->L * 0x1.0p-32;
-            for (size_t q = 0; q < spos.size(); ++q) positions_out[q] = (double)spos[q] * scale;
+            const double scale = sim->L * 0x1.0p-21;
+            for (int i = 0; i < N; ++i)
+                for (int d = 0; d < DIM; ++d)
+                    positions_out[(size_t)i * DIM + d] = (double)((spos[i] >> (21 * d)) & 0x1fffffu) * scale;
         }
     }
     for (int i = 0; i <= N; ++i) off_out[i] = (int32_t)off[i];

@@ -59,6 +59,24 @@ __device__ __forceinline__ double neg_log_u53(uint64_t k) {
     return __fma_rn((double)(53 - e), 0.6931471805599453, -logm);
 }
 
+// ---------------------------------------------------------------- waiting time dt = E / a0
+// Correctly rounded single-precision reciprocal refined by one Newton step in double (relative error
+// < 2^-45); IEEE operations only, so the mirror reproduces it bit for bit.  Outside the range where
+// the float reciprocal is normal the plain IEEE division is used.
+__device__ __forceinline__ double event_dt(double E, double a0) {
+    if (a0 < 1e-30 || a0 > 1e30) return __ddiv_rn(E, a0);
+    const double r = (double)__frcp_rn(__double2float_rn(a0));
+    const double y = __dmul_rn(E, r);
+    const double rem = __fma_rn(-a0, y, E);
+    return __fma_rn(rem, r, y);
+}
+
+// ---------------------------------------------------------------- lattice positions
+// 21 bits per axis (top bits of one Philox word each), packed k0 | k1 << 21 | k2 << 42;
+// x_d = k_d * L * 2^-21 in [0, L).
+constexpr int POS_BITS = 21;
+constexpr uint32_t POS_MASK = (1u << POS_BITS) - 1u;
+
 // ---------------------------------------------------------------- state word of one particle
 // sn = state | nA << 2 | nB << 17 ; state codes follow the reference (forward_simulator.jl:123):
 // 1 = A (free antigen), 2 = B (singly bound), 0 = C (member of a doubly bound pair).
@@ -72,7 +90,7 @@ __device__ __forceinline__ int sn_nB(uint32_t v) { return (int)(v >> SH_NB); }
 
 // ---------------------------------------------------------------- cell grid (shared with host)
 // nc cells per axis: min(floor(L/reach), cmax) where cmax is the largest c with c^DIM <= min(N,1024);
-// fewer than 3 cells per axis -> 1 (all-pairs).  Cell of lattice coordinate k: (k*nc) >> 32.
+// fewer than 3 cells per axis -> 1 (all-pairs).  Cell of lattice coordinate k: (k*nc) >> 21.
 __host__ __device__ inline int cells_per_axis(int N, int DIM, double L, double reach) {
     int cmax = 1;
     const long long lim = N < 1024 ? (N < 1 ? 1 : N) : 1024;

@@ -33,32 +33,32 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 }
 
 template <int DIM>
-__device__ __forceinline__ void gen_position(uint32_t i, uint32_t rep, uint32_t pidx, uint32_t k0,
-                                             uint32_t k1, uint32_t (&k)[DIM]) {
+__device__ __forceinline__ uint64_t gen_position(uint32_t i, uint32_t rep, uint32_t pidx, uint32_t k0, uint32_t k1) {
     const u32x4 r = philox4x32_10(i, STREAM_POSITIONS, rep, pidx, k0, k1);
-    k[0] = r.x;
-    k[1] = r.y;
-    if (DIM == 3) k[2] = r.z;
+    uint64_t p = (uint64_t)(r.x >> (32 - POS_BITS)) | ((uint64_t)(r.y >> (32 - POS_BITS)) << POS_BITS);
+    if (DIM == 3) p |= (uint64_t)(r.z >> (32 - POS_BITS)) << (2 * POS_BITS);
+    return p;
 }
 
+__device__ __forceinline__ uint32_t pos_axis(uint64_t p, int d) { return (uint32_t)(p >> (d * POS_BITS)) & POS_MASK; }
+
 template <int DIM>
-__device__ __forceinline__ uint32_t cell_of(const uint32_t (&k)[DIM], uint32_t nc) {
+__device__ __forceinline__ uint32_t cell_of(uint64_t p, uint32_t nc) {
     uint32_t c = 0;
 #pragma unroll
-    for (int d = DIM - 1; d >= 0; --d) c = c * nc + __umulhi(k[d], nc);
+    for (int d = DIM - 1; d >= 0; --d) c = c * nc + ((pos_axis(p, d) * nc) >> POS_BITS);
     return c;
 }
 
-// squared min-image distance on the 2^-32 L lattice, evaluated like periodic_dist_sq
+// squared min-image distance on the 2^-21 L lattice, evaluated like periodic_dist_sq
 // (forward_simulator.jl:1-8): exact integer min-image, then one rounding per product/accumulate.
 template <int DIM>
-__device__ __forceinline__ bool within_reach(const uint32_t (&a)[DIM], const uint32_t *b, double scale,
-                                             double reach2) {
+__device__ __forceinline__ bool within_reach(uint64_t a, uint64_t b, double scale, double reach2) {
     double acc = 0.0;
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
-        const uint32_t df = a[d] - b[d];
-        const uint32_t nd = 0u - df;
+        const uint32_t df = (pos_axis(a, d) - pos_axis(b, d)) & POS_MASK;
+        const uint32_t nd = (0u - df) & POS_MASK;
         const uint32_t m = df < nd ? df : nd;
         const double dd = __dmul_rn(__uint2double_rn(m), scale);
         acc = __fma_rn(dd, dd, acc);
@@ -92,8 +92,8 @@ struct Smem {
     void *off;
     uint32_t *sn;
     uint16_t *listA, *listB, *pos;
-    uint32_t *listC;
-    uint32_t *spos;
+    uint32_t *listC;   // last word of the array listA lives in: complexes grow downwards from it
+    uint64_t *spos;
     uint16_t *cstart;
     uint16_t *cfill;
     uint4 *rng;
@@ -109,7 +109,7 @@ __device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &l) 
     s.listB = reinterpret_cast<uint16_t *>(base + l.o_listB);
     s.pos = reinterpret_cast<uint16_t *>(base + l.o_pos);
     s.listC = reinterpret_cast<uint32_t *>(base + l.o_listC);
-    s.spos = reinterpret_cast<uint32_t *>(base + l.o_spos);
+    s.spos = reinterpret_cast<uint64_t *>(base + l.o_spos);
     s.cstart = reinterpret_cast<uint16_t *>(base + l.o_cstart);
     s.rng = reinterpret_cast<uint4 *>(base + l.o_rng);
     return s;
@@ -132,7 +132,7 @@ __device__ int build_table_resampled(const Smem &sm, int N, double L, double rea
     int ncell = nc;
 #pragma unroll
     for (int d = 1; d < DIM; ++d) ncell *= nc;
-    const double scale = __dmul_rn(L, 0x1.0p-32);
+    const double scale = __dmul_rn(L, 0x1.0p-21);
     const double reach2 = __dmul_rn(reach, reach);
 
     for (int c = lane; c <= ncell; c += 32) sm.cstart[c] = 0;
@@ -141,11 +141,7 @@ __device__ int build_table_resampled(const Smem &sm, int N, double L, double rea
     for (int base = 0; base < N; base += 32) {
         const int i = base + lane;
         uint32_t cell = 0x10000u + (uint32_t)lane;
-        if (i < N) {
-            uint32_t k[DIM];
-            gen_position<DIM>((uint32_t)i, rep, pidx, k0, k1, k);
-            cell = cell_of<DIM>(k, (uint32_t)nc);
-        }
+        if (i < N) cell = cell_of<DIM>(gen_position<DIM>((uint32_t)i, rep, pidx, k0, k1), (uint32_t)nc);
         const uint32_t mask = __match_any_sync(FULL, cell);
         if (i < N && (__ffs(mask) - 1) == lane) sm.cstart[cell + 1] += (uint16_t)__popc(mask);
         __syncwarp();
@@ -171,18 +167,17 @@ __device__ int build_table_resampled(const Smem &sm, int N, double L, double rea
     for (int base = 0; base < N; base += 32) {
         const int i = base + lane;
         uint32_t cell = 0x10000u + (uint32_t)lane;
-        uint32_t k[DIM];
+        uint64_t pk = 0;
         if (i < N) {
-            gen_position<DIM>((uint32_t)i, rep, pidx, k0, k1, k);
-            cell = cell_of<DIM>(k, (uint32_t)nc);
+            pk = gen_position<DIM>((uint32_t)i, rep, pidx, k0, k1);
+            cell = cell_of<DIM>(pk, (uint32_t)nc);
         }
         const uint32_t mask = __match_any_sync(FULL, cell);
         int slot = 0;
         if (i < N) slot = sm.cfill[cell] + __popc(mask & lanemask_lt());
         __syncwarp();
         if (i < N) {
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) sm.spos[slot * DIM + d] = k[d];
+            sm.spos[slot] = pk;
             if ((__ffs(mask) - 1) == lane) sm.cfill[cell] += (uint16_t)__popc(mask);
         }
         __syncwarp();
@@ -195,13 +190,10 @@ __device__ int build_table_resampled(const Smem &sm, int N, double L, double rea
         for (int base = 0; base < N; base += 32) {
             const int i = base + lane;
             if (i < N) {
-                uint32_t ki[DIM];
+                const uint64_t ki = sm.spos[i];
                 int ci[DIM];
 #pragma unroll
-                for (int d = 0; d < DIM; ++d) {
-                    ki[d] = sm.spos[i * DIM + d];
-                    ci[d] = (int)__umulhi(ki[d], (uint32_t)nc);
-                }
+                for (int d = 0; d < DIM; ++d) ci[d] = (int)((pos_axis(ki, d) * (uint32_t)nc) >> POS_BITS);
                 int cnt = 0;
                 int wp = pass ? (int)off[i] : 0;
                 const int zlo = DIM == 3 ? lo : 0, zhi = DIM == 3 ? hi : 0;
@@ -220,7 +212,7 @@ __device__ int build_table_resampled(const Smem &sm, int N, double L, double rea
                             const int cell = (cz * nc + cy) * nc + cx;
                             const int jb = sm.cstart[cell], je = sm.cstart[cell + 1];
                             for (int j = jb; j < je; ++j) {
-                                if (j != i && within_reach<DIM>(ki, sm.spos + j * DIM, scale, reach2)) {
+                                if (j != i && within_reach<DIM>(ki, sm.spos[j], scale, reach2)) {
                                     if (pass) sm.nbr[wp++] = (uint16_t)j;
                                     else ++cnt;
                                 }
@@ -248,19 +240,65 @@ __device__ int build_table_resampled(const Smem &sm, int N, double L, double rea
 // K1: the trajectory.  All scalars (time, counts, list lengths) are warp-uniform registers; the 32
 // lanes share the neighbour updates, list scans, bin writes and random-number generation.
 // ------------------------------------------------------------------------------------------------
-struct TrajState {
-    int cntA, cntB, cntC, nAB;
+
+// Neighbour updates are split into a load (row offset, degree, this lane's neighbour) and an apply
+// (read-modify-write of the neighbour's state word), so that the loads of both members of a pair
+// event are in flight together.  When the partner of a pair event (`other`) is met, its own state
+// change `extra` rides on the same store: pair events need no separate state write.
+struct NbrRow {
+    int o0, dg, j;   // first entry, degree, neighbour handled by this lane (valid if lane < dg)
 };
 
-// add `delta` to the state word of every neighbour of particle m (lanes stride the list)
 template <typename OffT>
-__device__ __forceinline__ void bump_neighbours(const Smem &sm, int m, uint32_t delta, int lane) {
-    const OffT *off = reinterpret_cast<const OffT *>(sm.off);
-    const int o0 = (int)off[m], o1 = (int)off[m + 1];
-    for (int q = o0 + lane; q < o1; q += 32) {
-        const int j = sm.nbr[q];
-        sm.sn[j] += delta;
+__device__ __forceinline__ NbrRow load_row(const Smem &sm, const OffT *off, int m, int lane) {
+    NbrRow r;
+    r.o0 = (int)off[m];
+    r.dg = (int)off[m + 1] - r.o0;
+    r.j = lane < r.dg ? (int)sm.nbr[r.o0 + lane] : 0;
+    return r;
+}
+
+template <bool PAIR>
+__device__ __forceinline__ void apply_row(const Smem &sm, const NbrRow &r, uint32_t delta, int other, uint32_t extra,
+                                          int lane) {
+    if (lane < r.dg) {
+        uint32_t d = delta;
+        if (PAIR && r.j == other) d += extra;
+        sm.sn[r.j] += d;
     }
+    if (r.dg > 32) {
+        for (int q = lane + 32; q < r.dg; q += 32) {
+            const int j = sm.nbr[r.o0 + q];
+            uint32_t d = delta;
+            if (PAIR && j == other) d += extra;
+            sm.sn[j] += d;
+        }
+    }
+}
+
+// inclusive scan over the first nact (<= 32) lanes, unrolled with warp-uniform early exit
+__device__ __forceinline__ int scan_small(int v, int lane, int nact) {
+    if (nact > 1) {
+        int o = __shfl_up_sync(FULL, v, 1);
+        if (lane >= 1) v += o;
+        if (nact > 2) {
+            o = __shfl_up_sync(FULL, v, 2);
+            if (lane >= 2) v += o;
+            if (nact > 4) {
+                o = __shfl_up_sync(FULL, v, 4);
+                if (lane >= 4) v += o;
+                if (nact > 8) {
+                    o = __shfl_up_sync(FULL, v, 8);
+                    if (lane >= 8) v += o;
+                    if (nact > 16) {
+                        o = __shfl_up_sync(FULL, v, 16);
+                        if (lane >= 16) v += o;
+                    }
+                }
+            }
+        }
+    }
+    return v;
 }
 
 template <int DIM, typename OffT>
@@ -319,25 +357,28 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
         const double koff = pt.koff, konb = pt.konb;
         const double kc = __dmul_rn(2.0, koff);           // C -> A+B rate (forward_simulator.jl:135)
         bool on = true;
+        bool last = false;
         int sidx = 0;
         double tp = tsave[0];
-        uint32_t ndraw = 0;
-        unsigned long long nev = 0;
+        // fast-path deadline: an event strictly before it needs no save-slot write, no switch-off and is
+        // not the last one
+        double tfast = fmin(fmin(tp, toff), tstop);
+        uint32_t ndraw = 0, nskip = 0;
         const size_t row = (size_t)slot * a.repstride + (size_t)(rep - a.rep_rowbase);
         uint16_t *crow = a.curve + row * (size_t)T;
         uint16_t *crow2 = a.curve2 ? a.curve2 + row * (size_t)T : nullptr;
         const int obs = a.observable;
 
         for (;;) {
-            // ---- randoms of this draw: {E = -log U (double), w2, w3}
+            // ---- randoms of this draw: {E = -log U (double), w2, w3}, generated 32 draws at a time
             if ((ndraw & 31u) == 0u) {
                 const u32x4 r = philox4x32_10(ndraw + (uint32_t)lane, STREAM_EVENTS, (uint32_t)rep, pidx,
                                               a.seed_lo, a.seed_hi);
                 const uint64_t k53 = (((uint64_t)r.x << 21) | (uint64_t)(r.y >> 11)) + 1ULL;
-                const double E = neg_log_u53(k53);
+                const double En = neg_log_u53(k53);
                 uint4 v;
-                v.x = (uint32_t)__double2loint(E);
-                v.y = (uint32_t)__double2hiint(E);
+                v.x = (uint32_t)__double2loint(En);
+                v.y = (uint32_t)__double2hiint(En);
                 v.z = r.z;
                 v.w = r.w;
                 __syncwarp();
@@ -353,40 +394,48 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
             const double cB = __dadd_rn(cA, __dmul_rn(koff, (double)cntB));
             const double cP = __dadd_rn(cB, __dmul_rn(konb, (double)nAB));
             const double a0 = __dadd_rn(cP, __dmul_rn(kc, (double)cntC));
-            double tn = a0 > 0.0 ? __dadd_rn(t, __ddiv_rn(E, a0)) : INF;
+            double tn = a0 > 0.0 ? __dadd_rn(t, event_dt(E, a0)) : INF;
 
-            // ---- antibody bath removed at tstop_AtoB (forward_simulator.jl:174-181, 199-202)
-            bool switched = false;
-            if (on && tn >= toff) {
-                tn = toff;
-                switched = true;
+            if (!(tn < tfast)) {
+                // ---- slow path: antibody bath removed at tstop_AtoB (forward_simulator.jl:174-181,
+                // 199-202), save slots strictly before the next event keep the current state (:188-194)
+                bool switched = false;
+                if (on && tn >= toff) {
+                    tn = toff;
+                    switched = true;
+                }
+                if (tn > tp) {
+                    const int xb = cntB + cntC;
+                    const uint16_t x1 = (uint16_t)(obs == OBS_TOTAL_A ? cntA : (obs == OBS_RAW_BC ? cntB : xb));
+                    int cnt;
+                    do {
+                        const int s = sidx + lane;
+                        const bool pred = (s < T) && (tsave[s] < tn);
+                        cnt = __popc(__ballot_sync(FULL, pred));
+                        if (pred) {
+                            crow[s] = x1;
+                            if (crow2) crow2[s] = (uint16_t)cntC;
+                        }
+                        sidx += cnt;
+                    } while (cnt == 32);
+                    tp = sidx < T ? tsave[sidx] : INF;
+                }
+                if (switched) {
+                    t = toff;
+                    kon = 0.0;
+                    on = false;
+                    ++nskip;
+                    tfast = fmin(tp, tstop);
+                    continue;
+                }
+                if (!(tn < INF)) {   // nothing can fire any more; all slots are filled
+                    ++nskip;
+                    break;
+                }
+                last = tn > tstop;   // the first event past tstop is still applied (:173, 183)
+                tfast = fmin(fmin(tp, on ? toff : INF), tstop);
             }
-            // ---- save slots strictly before the next event keep the current state (:188-194)
-            if (tn > tp) {
-                const int xb = cntB + cntC;
-                const uint16_t x1 = (uint16_t)(obs == OBS_TOTAL_A ? cntA : (obs == OBS_RAW_BC ? cntB : xb));
-                int cnt;
-                do {
-                    const int s = sidx + lane;
-                    const bool pred = (s < T) && (tsave[s] < tn);
-                    cnt = __popc(__ballot_sync(FULL, pred));
-                    if (pred) {
-                        crow[s] = x1;
-                        if (crow2) crow2[s] = (uint16_t)cntC;
-                    }
-                    sidx += cnt;
-                } while (cnt == 32);
-                tp = sidx < T ? tsave[sidx] : INF;
-            }
-            if (switched) {
-                t = toff;
-                kon = 0.0;
-                on = false;
-                continue;
-            }
-            if (!(tn < INF)) break;   // nothing can fire any more; all slots are filled
             t = tn;
-            ++nev;
 
             // ---- channel selection
             const double x = __dmul_rn(__dmul_rn((double)rv.z, 0x1.0p-32), a0);
@@ -394,35 +443,35 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
                 // A --> B (forward_simulator.jl:204-224)
                 const int k = (int)__umulhi(rv.w, (uint32_t)cntA);
                 const int m = sm.listA[k];
-                const int last = sm.listA[cntA - 1];
-                sm.listA[k] = (uint16_t)last;
-                sm.pos[last] = (uint16_t)k;
+                const int lastm = sm.listA[cntA - 1];
+                sm.listA[k] = (uint16_t)lastm;
+                sm.pos[lastm] = (uint16_t)k;
                 --cntA;
                 sm.listB[cntB] = (uint16_t)m;
                 sm.pos[m] = (uint16_t)cntB;
                 ++cntB;
                 const uint32_t v = sm.sn[m];
                 nAB += sn_nA(v) - sn_nB(v);
-                __syncwarp();
-                if (lane == 0) sm.sn[m] = (v & ~3u) | ST_B;
-                bump_neighbours<OffT>(sm, m, (1u << SH_NB) - (1u << SH_NA), lane);
+                sm.sn[m] = (v & ~3u) | ST_B;                        // idempotent: every lane stores the same word
+                const NbrRow row = load_row<OffT>(sm, off, m, lane);
+                apply_row<false>(sm, row, (1u << SH_NB) - (1u << SH_NA), 0, 0u, lane);
                 __syncwarp();
             } else if (x < cB) {
                 // B --> A (:228-253)
                 const int k = (int)__umulhi(rv.w, (uint32_t)cntB);
                 const int m = sm.listB[k];
-                const int last = sm.listB[cntB - 1];
-                sm.listB[k] = (uint16_t)last;
-                sm.pos[last] = (uint16_t)k;
+                const int lastm = sm.listB[cntB - 1];
+                sm.listB[k] = (uint16_t)lastm;
+                sm.pos[lastm] = (uint16_t)k;
                 --cntB;
                 sm.listA[cntA] = (uint16_t)m;
                 sm.pos[m] = (uint16_t)cntA;
                 ++cntA;
                 const uint32_t v = sm.sn[m];
                 nAB += sn_nB(v) - sn_nA(v);
-                __syncwarp();
-                if (lane == 0) sm.sn[m] = (v & ~3u) | ST_A;
-                bump_neighbours<OffT>(sm, m, (1u << SH_NA) - (1u << SH_NB), lane);
+                sm.sn[m] = (v & ~3u) | ST_A;
+                const NbrRow row = load_row<OffT>(sm, off, m, lane);
+                apply_row<false>(sm, row, (1u << SH_NA) - (1u << SH_NB), 0, 0u, lane);
                 __syncwarp();
             } else if (x < cP) {
                 // A + B --> C (:256-289): pair number k of the nAB active pairs, enumerated along the
@@ -442,7 +491,7 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
                         xm = list[idx];
                         w = (int)((sm.sn[xm] >> sh) & CNT_MASK);
                     }
-                    const int incl = warp_incl_scan(w, lane, nact);
+                    const int incl = scan_small(w, lane, nact);
                     const int tot = __shfl_sync(FULL, incl, nact - 1);
                     if (k < tot) {
                         const uint32_t hit = __ballot_sync(FULL, k < incl);
@@ -490,26 +539,25 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
                     sm.listB[ib] = (uint16_t)lastB;
                     sm.pos[lastB] = (uint16_t)ib;
                     --cntB;
-                    sm.listC[cntC] = (uint32_t)ma | ((uint32_t)mb << 16);
+                    *(sm.listC - cntC) = (uint32_t)ma | ((uint32_t)mb << 16);
                     ++cntC;
                 }
                 const uint32_t va = sm.sn[ma], vb = sm.sn[mb];
+                const NbrRow rowa = load_row<OffT>(sm, off, ma, lane);
+                const NbrRow rowb = load_row<OffT>(sm, off, mb, lane);
                 nAB -= sn_nB(va) + sn_nA(vb) - 1;
+                __syncwarp();   // every lane has read va, vb before the partner words change
+                // a's neighbours lose an A neighbour, and b (one of them) drops B(2) -> C(0);
+                // b's neighbours lose a B neighbour, and a drops A(1) -> C(0)
+                apply_row<true>(sm, rowa, 0u - (1u << SH_NA), mb, 0u - 2u, lane);
                 __syncwarp();
-                if (lane == 0) {
-                    sm.sn[ma] = (va & ~3u) | ST_C;
-                    sm.sn[mb] = (vb & ~3u) | ST_C;
-                }
-                __syncwarp();
-                bump_neighbours<OffT>(sm, ma, 0u - (1u << SH_NA), lane);
-                __syncwarp();
-                bump_neighbours<OffT>(sm, mb, 0u - (1u << SH_NB), lane);
+                apply_row<true>(sm, rowb, 0u - (1u << SH_NB), ma, 0u - 1u, lane);
                 __syncwarp();
             } else {
                 // C --> A + B (:291-344): complex k; the freed end is chosen by a fair coin (:300-307)
                 const int k = (int)__umulhi(rv.w, (uint32_t)cntC);
-                const uint32_t pr = sm.listC[k];
-                sm.listC[k] = sm.listC[cntC - 1];
+                const uint32_t pr = *(sm.listC - k);
+                *(sm.listC - k) = *(sm.listC - (cntC - 1));
                 --cntC;
                 int ma = (int)(pr & 0xffffu), mb = (int)(pr >> 16);
                 if (rv.w & 1u) {
@@ -524,19 +572,18 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
                 sm.pos[mb] = (uint16_t)cntB;
                 ++cntB;
                 const uint32_t va = sm.sn[ma], vb = sm.sn[mb];
+                const NbrRow rowa = load_row<OffT>(sm, off, ma, lane);
+                const NbrRow rowb = load_row<OffT>(sm, off, mb, lane);
                 nAB += sn_nB(va) + sn_nA(vb) + 1;
                 __syncwarp();
-                if (lane == 0) {
-                    sm.sn[ma] = (va & ~3u) | ST_A;
-                    sm.sn[mb] = (vb & ~3u) | ST_B;
-                }
+                // a's neighbours gain an A neighbour, and b becomes B: C(0) -> B(2);
+                // b's neighbours gain a B neighbour, and a becomes A: C(0) -> A(1)
+                apply_row<true>(sm, rowa, 1u << SH_NA, mb, 2u, lane);
                 __syncwarp();
-                bump_neighbours<OffT>(sm, ma, 1u << SH_NA, lane);
-                __syncwarp();
-                bump_neighbours<OffT>(sm, mb, 1u << SH_NB, lane);
+                apply_row<true>(sm, rowb, 1u << SH_NB, ma, 1u, lane);
                 __syncwarp();
             }
-            if (t > tstop) break;   // the first event past tstop is still applied (:173, 183)
+            if (last) break;
         }
         // ---- remaining save slots take the final state (forward_simulator.jl:349-354)
         {
@@ -547,7 +594,7 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
                 if (crow2) crow2[s] = (uint16_t)cntC;
             }
         }
-        if (lane == 0) atomicAdd(a.nevents + slot, nev);
+        if (lane == 0) atomicAdd(a.nevents + slot, (unsigned long long)(ndraw - nskip));
         __syncwarp();
     }
 }
@@ -556,7 +603,7 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
 template <int DIM, typename OffT>
 __global__ void __launch_bounds__(32) spr_table_dump_kernel(const TrajArgs a, uint32_t rep, int slot,
                                                             uint32_t *off_out, uint16_t *nbr_out,
-                                                            uint32_t *spos_out, long long *total_out) {
+                                                            uint64_t *spos_out, long long *total_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const Smem sm = carve(smem_raw, a.lay);
@@ -569,7 +616,7 @@ __global__ void __launch_bounds__(32) spr_table_dump_kernel(const TrajArgs a, ui
     const OffT *off = reinterpret_cast<const OffT *>(sm.off);
     for (int i = lane; i <= a.N; i += 32) off_out[i] = (uint32_t)off[i];
     for (int q = lane; q < entries; q += 32) nbr_out[q] = sm.nbr[q];
-    for (int q = lane; q < a.N * DIM; q += 32) spos_out[q] = sm.spos[q];
+    for (int q = lane; q < a.N; q += 32) spos_out[q] = sm.spos[q];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -765,6 +812,7 @@ inline int align16(int x) { return (x + 15) & ~15; }
 }  // namespace
 
 SmemLayout make_layout(int N, int DIM, int cap) {
+    (void)DIM;
     SmemLayout l;
     // cfill (u16 per cell, <= 1024 cells) aliases nbr during setup
     if (cap < 1024) cap = 1024;
@@ -776,16 +824,19 @@ SmemLayout make_layout(int N, int DIM, int cap) {
     l.o_off = o;
     o += align16((N + 1) * (l.wide_off ? 4 : 2));
     l.o_region = o;
-    // state view
+    // state view: the A list (u16, from the front) and the complex list (u32 pairs, from the back) share
+    // one array of 2N bytes: cntA + 2 cntC <= N always
     int s = o;
     l.o_sn = s;      s += align16(N * 4);
-    l.o_listA = s;   s += align16(N * 2);
+    l.o_listA = s;
+    const int ac_words = (2 * N + 3) / 4;
+    l.o_listC = s + 4 * (ac_words - 1);          // address of the LAST word
+    s += align16(4 * ac_words);
     l.o_listB = s;   s += align16(N * 2);
     l.o_pos = s;     s += align16(N * 2);
-    l.o_listC = s;   s += align16((N / 2 + 1) * 4);
-    // setup view
+    // setup view: packed lattice positions (8 B per particle) and the cell starts
     int u = o;
-    l.o_spos = u;    u += align16(N * DIM * 4);
+    l.o_spos = u;    u += align16(N * 8);
     l.o_cstart = u;  u += align16((1024 + 2) * 2);
     o = s > u ? s : u;
     l.o_rng = o;
@@ -835,7 +886,7 @@ int traj_blocks_per_sm(const SmemLayout &lay, int DIM) {
 }
 
 cudaError_t launch_table_dump(const TrajArgs &a, int DIM, uint32_t replicate, int slot, uint32_t *d_off_out,
-                              uint16_t *d_nbr_out, uint32_t *d_spos_out, long long *d_total_out,
+                              uint16_t *d_nbr_out, uint64_t *d_spos_out, long long *d_total_out,
                               cudaStream_t st) {
     return dispatch(DIM, a.lay.wide_off, [&](auto dim_c, auto off_t) -> cudaError_t {
         constexpr int D_ = decltype(dim_c)::value;

@@ -19,8 +19,8 @@ struct SmemLayout {
     int o_listA;   // u16[N]      particles in state A
     int o_listB;   // u16[N]      particles in state B
     int o_pos;     // u16[N]      index of a particle in listA/listB
-    int o_listC;   // u32[N/2+1]  complexes, a | b<<16
-    int o_spos;    // u32[N*DIM]  (setup) lattice positions, cell-sorted
+    int o_listC;   // u32         LAST word of the array shared with listA; complexes (a | b<<16) grow down
+    int o_spos;    // u64[N]      (setup) packed 21-bit lattice positions, cell-sorted
     int o_cstart;  // u16[ncell+1](setup) first sorted index of every cell
     int o_rng;     // 32 x 16 B   block of pre-generated event randoms
     int total;     // bytes of dynamic shared memory
@@ -68,7 +68,7 @@ cudaError_t launch_fixed_graph(const double *d_locs, int N, int DIM, double L, d
 
 // one-trajectory neighbour-table dump (test hook)
 cudaError_t launch_table_dump(const TrajArgs &a, int DIM, uint32_t replicate, int slot,
-                              uint32_t *d_off_out, uint16_t *d_nbr_out, uint32_t *d_spos_out,
+                              uint32_t *d_off_out, uint16_t *d_nbr_out, uint64_t *d_spos_out,
                               long long *d_total_out, cudaStream_t st);
 
 // K3: replicate reduction / sequential-stop scan

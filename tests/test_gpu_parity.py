@@ -32,13 +32,9 @@ def gpu_moments(engine, sim, point, nsims, seed, N, pidx=0, obs=0):
 def ref_moments(point, N, DIM, L, tstop, toff, tsave, nrep, seed, copies=None):
     """reference-algorithm oracle, replicates split over `copies` independent streams (one per core)"""
     from oracle import ref_oracle as R
-    copies = copies or min(os.cpu_count() or 1, 32)
+    copies = copies or 8          # fixed: the oracle sample must not depend on the host's core count
     per = max(2, -(-nrep // copies))
     sim = R.make_sim(N=N, DIM=DIM, tstop=tstop, tstop_AtoB=toff, tsave=tsave, L=L, nsims=per)
-    import ctypes as C
-    pts = np.tile(np.asarray(point, dtype=np.float64), (copies, 1))
-    # per-copy mean only comes back from run_points; get variance via the single-point API on each stream
-    means = np.zeros((copies, len(tsave))); vars_ = np.zeros((copies, len(tsave))); ev = 0
     from concurrent.futures import ThreadPoolExecutor
 
     def one(c):
