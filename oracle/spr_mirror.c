@@ -118,16 +118,25 @@ typedef struct {
     int nbr_cap, entries;
 } table_t;
 
-static int within(const uint32_t *a, const uint32_t *b, int DIM, double scale, double reach2) {
-    double acc = 0.0;
+/* exact squared min-image distance in lattice units vs r2lat = floor(reach^2 / (L 2^-21)^2) */
+static int within(const uint32_t *a, const uint32_t *b, int DIM, uint64_t r2lat) {
+    uint64_t acc = 0;
     for (int d = 0; d < DIM; d++) {
         uint32_t df = (a[d] - b[d]) & POS_MASK;
         uint32_t nd = (0u - df) & POS_MASK;
-        uint32_t m = df < nd ? df : nd;
-        double dd = (double)m * scale;
-        acc = fma(dd, dd, acc);
+        uint64_t m = df < nd ? df : nd;
+        acc += m * m;
     }
-    return acc <= reach2;
+    return acc <= r2lat;
+}
+
+static uint64_t reach2_lattice(double L, double reach) {
+    double scale = L * 0x1.0p-21;
+    double num = reach * reach;
+    double den = scale * scale;
+    double q = num / den;
+    if (!(q < 4611686018427387904.0)) return 4611686018427387904ULL;
+    return (uint64_t)q;
 }
 
 static void table_push(table_t *t, int j) {
@@ -145,8 +154,7 @@ static void build_table_resampled(table_t *t, double L, double reach, uint32_t r
     const int nc = spr_mirror_cells_per_axis(N, DIM, L, reach);
     int ncell = 1;
     for (int d = 0; d < DIM; d++) ncell *= nc;
-    const double scale = L * 0x1.0p-21;
-    const double reach2 = reach * reach;
+    const uint64_t r2lat = reach2_lattice(L, reach);
     uint32_t *raw = (uint32_t *)malloc(sizeof(uint32_t) * N * DIM);
     int *cell = (int *)malloc(sizeof(int) * N);
     int *cstart = (int *)calloc(ncell + 1, sizeof(int));
@@ -183,7 +191,7 @@ static void build_table_resampled(table_t *t, double L, double reach, uint32_t r
                     int cx = ci[0] + dx; cx = cx < 0 ? cx + nc : (cx >= nc ? cx - nc : cx);
                     int c = (cz * nc + cy) * nc + cx;
                     for (int j = cstart[c]; j < cstart[c + 1]; j++)
-                        if (j != i && within(ki, t->spos + j * DIM, DIM, scale, reach2)) table_push(t, j);
+                        if (j != i && within(ki, t->spos + j * DIM, DIM, r2lat)) table_push(t, j);
                 }
             }
         }

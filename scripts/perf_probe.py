@@ -17,6 +17,9 @@ def run(name, pt, nsims, tstop=600.0, toff=150.0, T=601):
     print("%-34s traj %6d ev/traj %9.1f  dev %8.2f ms  %8.2f us/traj  ev/s %.3e" %
           (name, nsims, ev / nsims, ms, ms * 1e3 / nsims, ev / (ms * 1e-3)), flush=True)
 only = sys.argv[1] if len(sys.argv) > 1 else ""
+if only == "ncusetup":
+    run("ncu: setup only reach 15.3", [0.0, 0.1, 1.0, 15.29], 2072)
+    sys.exit(0)
 if only == "ncu":
     run("ncu: pingpong reach35", [1.0, 0.1, 3.0, 35.0], 592, tstop=200.0, toff=100.0, T=201)
     sys.exit(0)

@@ -298,8 +298,13 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
             // order arrays for all classes packed into one upload
             h_order.clear();
             std::vector<size_t> class_off;
-            for (auto &kv : classes) {
-                ClassWork &cw = kv.second;
+            // widest tables first: those classes run the fewest trajectories per SM and finish last, the
+            // cheap small-reach classes then fill the SMs as the wide ones drain
+            std::vector<std::pair<const std::pair<int, int>, ClassWork> *> ordered;
+            for (auto &kv : classes) ordered.push_back(&kv);
+            std::reverse(ordered.begin(), ordered.end());
+            for (auto *kvp : ordered) {
+                ClassWork &cw = kvp->second;
                 std::vector<std::pair<double, int32_t>> keyed;
                 keyed.reserve(cw.slots.size());
                 for (int32_t sl : cw.slots)
@@ -315,9 +320,9 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
             struct Launched { int cap; size_t ci; SmemLayout lay; TrajArgs args; };
             std::vector<Launched> launched;
             size_t ci = 0;
-            for (auto &kv : classes) {
-                const int cap = kv.first.first;
-                ClassWork &cw = kv.second;
+            for (auto *kvp : ordered) {
+                const int cap = kvp->first.first;
+                ClassWork &cw = kvp->second;
                 SmemLayout lay = make_layout(N, DIM, cap);
                 if (lay.total > h->smem_optin) {
                     free_graphs();

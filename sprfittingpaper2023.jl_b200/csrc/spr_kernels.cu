@@ -50,20 +50,28 @@ __device__ __forceinline__ uint32_t cell_of(uint64_t p, uint32_t nc) {
     return c;
 }
 
-// squared min-image distance on the 2^-21 L lattice, evaluated like periodic_dist_sq
-// (forward_simulator.jl:1-8): exact integer min-image, then one rounding per product/accumulate.
+// Squared min-image distance in lattice units, exact in 64-bit integers (each axis < 2^20, so the sum
+// is < 2^42), compared with r2lat = floor(reach^2 / (L 2^-21)^2): the reference's test
+// periodic_dist_sq <= reach^2 (forward_simulator.jl:1-8, 54-55) evaluated without rounding on the lattice.
 template <int DIM>
-__device__ __forceinline__ bool within_reach(uint64_t a, uint64_t b, double scale, double reach2) {
-    double acc = 0.0;
+__device__ __forceinline__ bool within_reach(uint64_t a, uint64_t b, unsigned long long r2lat) {
+    unsigned long long acc = 0;
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
         const uint32_t df = (pos_axis(a, d) - pos_axis(b, d)) & POS_MASK;
         const uint32_t nd = (0u - df) & POS_MASK;
         const uint32_t m = df < nd ? df : nd;
-        const double dd = __dmul_rn(__uint2double_rn(m), scale);
-        acc = __fma_rn(dd, dd, acc);
+        acc += (unsigned long long)m * m;
     }
-    return acc <= reach2;
+    return acc <= r2lat;
+}
+
+// r2lat of the specification: floor(reach^2 / scale^2) with scale = L 2^-21, clamped to 2^62
+__host__ __device__ inline unsigned long long reach2_lattice(double L, double reach) {
+    const double scale = L * 0x1.0p-21;
+    const double q = (reach * reach) / (scale * scale);   // separate IEEE operations (no contraction)
+    if (!(q < 4611686018427387904.0)) return 4611686018427387904ULL;
+    return (unsigned long long)q;                        // truncation == floor for q >= 0
 }
 
 // in-place exclusive prefix sum of a[0..n) (values < 2^31 in total), returns the total.
@@ -132,8 +140,7 @@ __device__ int build_table_resampled(const Smem &sm, int N, double L, double rea
     int ncell = nc;
 #pragma unroll
     for (int d = 1; d < DIM; ++d) ncell *= nc;
-    const double scale = __dmul_rn(L, 0x1.0p-21);
-    const double reach2 = __dmul_rn(reach, reach);
+    const unsigned long long r2lat = reach2_lattice(L, reach);
 
     for (int c = lane; c <= ncell; c += 32) sm.cstart[c] = 0;
     __syncwarp();
@@ -182,8 +189,11 @@ __device__ int build_table_resampled(const Smem &sm, int N, double L, double rea
         }
         __syncwarp();
     }
-    // passes 3 (count) and 4 (fill): one particle per lane, cells in (dz,dy,dx) order
-    const int lo = nc >= 3 ? -1 : 0, hi = nc >= 3 ? 1 : 0;
+    // passes 3 (count) and 4 (fill): one particle per lane.  Candidates come from the 3^DIM cells around
+    // the particle in (dz,dy,dx) order; the three x-cells of a (dz,dy) row are contiguous in the sorted
+    // numbering except across the periodic wrap, so a row is one or two index ranges.  The loop is
+    // flattened over (row, range, candidate) to keep the 32 lanes busy despite unequal cell fillings.
+    const int nrow = nc >= 3 ? (DIM == 3 ? 9 : 3) : 1;
     int total = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
@@ -191,33 +201,45 @@ __device__ int build_table_resampled(const Smem &sm, int N, double L, double rea
             const int i = base + lane;
             if (i < N) {
                 const uint64_t ki = sm.spos[i];
-                int ci[DIM];
-#pragma unroll
-                for (int d = 0; d < DIM; ++d) ci[d] = (int)((pos_axis(ki, d) * (uint32_t)nc) >> POS_BITS);
+                const int cx = (int)((pos_axis(ki, 0) * (uint32_t)nc) >> POS_BITS);
+                const int cy = (int)((pos_axis(ki, 1) * (uint32_t)nc) >> POS_BITS);
+                const int cz = DIM == 3 ? (int)((pos_axis(ki, 2) * (uint32_t)nc) >> POS_BITS) : 0;
                 int cnt = 0;
                 int wp = pass ? (int)off[i] : 0;
-                const int zlo = DIM == 3 ? lo : 0, zhi = DIM == 3 ? hi : 0;
-                for (int dz = zlo; dz <= zhi; ++dz) {
-                    int cz = 0;
-                    if (DIM == 3) {
-                        cz = ci[DIM - 1] + dz;
-                        cz = cz < 0 ? cz + nc : (cz >= nc ? cz - nc : cz);
-                    }
-                    for (int dy = lo; dy <= hi; ++dy) {
-                        int cy = ci[1] + dy;
-                        cy = cy < 0 ? cy + nc : (cy >= nc ? cy - nc : cy);
-                        for (int dx = lo; dx <= hi; ++dx) {
-                            int cx = ci[0] + dx;
-                            cx = cx < 0 ? cx + nc : (cx >= nc ? cx - nc : cx);
-                            const int cell = (cz * nc + cy) * nc + cx;
-                            const int jb = sm.cstart[cell], je = sm.cstart[cell + 1];
-                            for (int j = jb; j < je; ++j) {
-                                if (j != i && within_reach<DIM>(ki, sm.spos[j], scale, reach2)) {
-                                    if (pass) sm.nbr[wp++] = (uint16_t)j;
-                                    else ++cnt;
-                                }
+                int r = 0, h = 0, j = 0, je = 0;
+                for (;;) {
+                    if (j < je) {
+                        if (j != i && within_reach<DIM>(ki, sm.spos[j], r2lat)) {
+                            if (pass) sm.nbr[wp++] = (uint16_t)j;
+                            else ++cnt;
+                        }
+                        ++j;
+                    } else {
+                        if (r == nrow) break;
+                        int ca, cb;
+                        if (nc < 3) {
+                            ca = 0; cb = 1; ++r;
+                        } else {
+                            int yy = cy + (DIM == 3 ? r % 3 : r) - 1;
+                            yy = yy < 0 ? yy + nc : (yy >= nc ? yy - nc : yy);
+                            int zz = 0;
+                            if (DIM == 3) {
+                                zz = cz + r / 3 - 1;
+                                zz = zz < 0 ? zz + nc : (zz >= nc ? zz - nc : zz);
+                            }
+                            const int rb = (zz * nc + yy) * nc;
+                            if (cx == 0) {
+                                if (h == 0) { ca = rb + nc - 1; cb = rb + nc; h = 1; }
+                                else { ca = rb; cb = rb + 2; h = 0; ++r; }
+                            } else if (cx == nc - 1) {
+                                if (h == 0) { ca = rb + nc - 2; cb = rb + nc; h = 1; }
+                                else { ca = rb; cb = rb + 1; h = 0; ++r; }
+                            } else {
+                                ca = rb + cx - 1; cb = rb + cx + 2; ++r;
                             }
                         }
+                        j = sm.cstart[ca];
+                        je = sm.cstart[cb];
                     }
                 }
                 if (!pass) off[i] = (OffT)cnt;   // degree < 65536 always (N <= 65535)
