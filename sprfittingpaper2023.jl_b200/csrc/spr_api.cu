@@ -59,12 +59,18 @@ struct sprb200_ctx {
     std::string err;
     // arenas
     DevBuf tsave, pts, pidx, order, curve, curve2, sum, sumsq, nused, nevents, nscanned, nstar, active, counters,
-        ovf, rows, locs, goff, gnbr, misc, table;
+        ovf, rows, locs, goff, gnbr, misc, table, nbrscratch, nbrscratch2;
     // stats of the last call
     uint64_t st_traj = 0, st_events = 0, st_launches = 0;
     double st_ms = 0.0;
     size_t curve_budget = (size_t)8 << 30;
     double cap_scale = 1.0;   // SPRB200_CAP_SCALE (test hook): shrinks the a-priori table capacity
+    // Tables of at least this many entries live in global memory (L2-resident, one slice per CTA) instead
+    // of shared memory: the extra L2 latency per row is outweighed by 16 instead of 5-14 resident
+    // trajectories per SM.  Measured on B200 (profiles/README.md): global wins for every reach class of
+    // the surrogate grids, so the default is 0; SPRB200_NBR_GLOBAL_MIN_CAP overrides (1e9 = always shared).
+    long long nbr_global_min_cap = 0;
+    size_t nbr_scratch_budget = (size_t)6 << 30;
 };
 
 namespace {
@@ -172,6 +178,17 @@ struct ClassWork {
     SmemLayout lay;
     std::vector<int32_t> slots;   // sorted expensive-first
 };
+
+// table placement for a class: shared memory if it fits and the table is small, else global memory
+bool choose_layout(const sprb200_ctx *h, int N, int DIM, int cap, SmemLayout *out) {
+    const SmemLayout ls = make_layout(N, DIM, cap, false);
+    const SmemLayout lg = make_layout(N, DIM, cap, true);
+    if (ls.total <= h->smem_optin && (long long)cap < h->nbr_global_min_cap) { *out = ls; return true; }
+    if (lg.total <= h->smem_optin) { *out = lg; return true; }
+    if (ls.total <= h->smem_optin) { *out = ls; return true; }
+    *out = lg;
+    return false;
+}
 
 // Simulates `npts` points (already on the host as PointDev + pidx).  On return the device arenas hold
 // sum/sumsq [npts][T], nused [npts], nevents [npts] (and curve/curve2 when plan.raw for a single
@@ -319,18 +336,41 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
 
             struct Launched { int cap; size_t ci; SmemLayout lay; TrajArgs args; };
             std::vector<Launched> launched;
-            size_t ci = 0;
+            struct Prep { int cap; ClassWork *cw; SmemLayout lay; long long nblocks; size_t scratch_off; };
+            std::vector<Prep> preps;
+            size_t scratch_total = 0;
             for (auto *kvp : ordered) {
                 const int cap = kvp->first.first;
                 ClassWork &cw = kvp->second;
-                SmemLayout lay = make_layout(N, DIM, cap);
-                if (lay.total > h->smem_optin) {
+                SmemLayout lay;
+                if (!choose_layout(h, N, DIM, cap, &lay)) {
                     free_graphs();
                     return fail(h, SPRB200_ERR_TOO_LARGE,
-                                "neighbour table of " + std::to_string(cap) + " entries (N=" + std::to_string(N) +
-                                    ") needs " + std::to_string(lay.total) + " B of shared memory per trajectory, limit " +
+                                "per-trajectory state (N=" + std::to_string(N) + ", table of " + std::to_string(cap) +
+                                    " entries) needs " + std::to_string(lay.total) + " B of shared memory, limit " +
                                     std::to_string(h->smem_optin));
                 }
+                const int bps = traj_blocks_per_sm(lay, DIM);
+                if (bps < 1) { free_graphs(); return fail(h, SPRB200_ERR_TOO_LARGE, "trajectory kernel does not fit on an SM"); }
+                const long long ntick = (long long)cw.slots.size() * (rep_hi - rep_lo);
+                long long nblocks = std::min<long long>(ntick, (long long)bps * h->num_sms);
+                size_t off = 0;
+                if (lay.nbr_global) {
+                    const size_t per = (size_t)lay.cap * sizeof(uint16_t);
+                    const long long fit = (long long)std::max<size_t>(1, h->nbr_scratch_budget / per);
+                    nblocks = std::min(nblocks, fit);
+                    off = scratch_total;
+                    scratch_total += (size_t)nblocks * per;
+                    scratch_total = (scratch_total + 255) & ~(size_t)255;
+                }
+                preps.push_back(Prep{cap, &cw, lay, nblocks, off});
+            }
+            if (scratch_total) CUDA_TRY(h, h->nbrscratch.ensure(scratch_total));
+            size_t ci = 0;
+            for (auto &pr : preps) {
+                const int cap = pr.cap;
+                ClassWork &cw = *pr.cw;
+                const SmemLayout &lay = pr.lay;
                 TrajArgs a{};
                 a.N = N; a.T = T; a.L = sim->L; a.tstop = sim->tstop; a.toff = sim->tstop_AtoB;
                 a.tsave = h->tsave.as<double>();
@@ -349,17 +389,15 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                 a.ovf_list = h->ovf.as<long long>() + (size_t)ovf_cap * ci;
                 a.ovf_count = reinterpret_cast<unsigned int *>(h->counters.as<unsigned long long>() + 2 * ci + 1);
                 a.ovf_cap = ovf_cap;
+                a.nbr_scratch = lay.nbr_global ? reinterpret_cast<uint16_t *>(h->nbrscratch.as<unsigned char>() + pr.scratch_off) : nullptr;
                 if (!sim->resample_initlocs) {
                     const FixedGraph &g = graphs[pts[b0 + cw.slots[0]].reach];
                     a.g_off = g.off; a.g_nbr = g.nbr;
                 }
                 a.lay = lay;
-                const int bps = traj_blocks_per_sm(lay, DIM);
-                if (bps < 1) { free_graphs(); return fail(h, SPRB200_ERR_TOO_LARGE, "trajectory kernel does not fit on an SM"); }
-                const long long nblocks = std::min<long long>(a.ntickets, (long long)bps * h->num_sms);
                 cudaStream_t st = h->stream[ci % NSTREAM];
                 if (st != s0) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_ready, 0));
-                CUDA_TRY(h, launch_traj(a, DIM, (int)nblocks, st));
+                CUDA_TRY(h, launch_traj(a, DIM, (int)pr.nblocks, st));
                 h->st_launches += 1;
                 h->st_traj += (uint64_t)a.ntickets;
                 launched.push_back(Launched{cap, ci, lay, a});
@@ -382,10 +420,10 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                     const long long maxe = (long long)N * (N - 1);
                     if (cap >= maxe) { free_graphs(); return fail(h, SPRB200_ERR_INTERNAL, "overflow at full capacity"); }
                     cap = (int)std::min<long long>(maxe + 64, (long long)cap + cap / 4 + 512);
-                    SmemLayout lay = make_layout(N, DIM, cap);
-                    if (lay.total > h->smem_optin) {
+                    SmemLayout lay;
+                    if (!choose_layout(h, N, DIM, cap, &lay)) {
                         free_graphs();
-                        return fail(h, SPRB200_ERR_TOO_LARGE, "neighbour table does not fit in shared memory after overflow");
+                        return fail(h, SPRB200_ERR_TOO_LARGE, "per-trajectory state does not fit in shared memory after overflow");
                     }
                     // move the overflow list aside (misc) and reuse the class's counters
                     CUDA_TRY(h, h->misc.ensure(sizeof(long long) * novf + 64));
@@ -398,7 +436,15 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                     a.ntickets = novf;
                     const int bps = traj_blocks_per_sm(lay, DIM);
                     if (bps < 1) { free_graphs(); return fail(h, SPRB200_ERR_TOO_LARGE, "trajectory kernel does not fit on an SM"); }
-                    CUDA_TRY(h, launch_traj(a, DIM, (int)std::min<long long>(novf, (long long)bps * h->num_sms), s0));
+                    long long nblk = std::min<long long>(novf, (long long)bps * h->num_sms);
+                    if (lay.nbr_global) {
+                        const size_t per = (size_t)lay.cap * sizeof(uint16_t);
+                        nblk = std::min<long long>(nblk, (long long)std::max<size_t>(1, h->nbr_scratch_budget / per));
+                        CUDA_TRY(h, h->nbrscratch2.ensure((size_t)nblk * per));
+                        a.nbr_scratch = h->nbrscratch2.as<uint16_t>();
+                    } else
+                        a.nbr_scratch = nullptr;
+                    CUDA_TRY(h, launch_traj(a, DIM, (int)nblk, s0));
                     h->st_launches += 1;
                     unsigned long long cnt2[2] = {0, 0};
                     CUDA_TRY(h, cudaMemcpyAsync(cnt2, lc.args.ticket_ctr, sizeof(cnt2), cudaMemcpyDeviceToHost, s0));
@@ -570,6 +616,10 @@ int sprb200_create(int device_ordinal, sprb200_handle *out) {
         const long long v = std::atoll(env);
         if (v > 0) h->curve_budget = (size_t)v;
     }
+    if (const char *env = std::getenv("SPRB200_NBR_GLOBAL_MIN_CAP")) {
+        const long long v = std::atoll(env);
+        if (v >= 0) h->nbr_global_min_cap = v;
+    }
     if (const char *env = std::getenv("SPRB200_CAP_SCALE")) {
         const double v = std::atof(env);
         if (v > 0.0 && v <= 1.0) h->cap_scale = v;
@@ -586,7 +636,7 @@ void sprb200_destroy(sprb200_handle h) {
     }
     DevBuf *bufs[] = {&h->tsave, &h->pts, &h->pidx, &h->order, &h->curve, &h->curve2, &h->sum, &h->sumsq, &h->nused,
                       &h->nevents, &h->nscanned, &h->nstar, &h->active, &h->counters, &h->ovf, &h->rows, &h->locs,
-                      &h->goff, &h->gnbr, &h->misc, &h->table};
+                      &h->goff, &h->gnbr, &h->misc, &h->table, &h->nbrscratch, &h->nbrscratch2};
     for (DevBuf *b : bufs) b->release();
     for (int s = 0; s < NSTREAM; ++s) {
         if (h->ev_done[s]) cudaEventDestroy(h->ev_done[s]);

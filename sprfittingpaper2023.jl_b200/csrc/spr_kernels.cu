@@ -107,10 +107,11 @@ struct Smem {
     uint4 *rng;
 };
 
-__device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &l) {
+template <bool NBRG>
+__device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &l, uint16_t *nbr_scratch) {
     Smem s;
-    s.nbr = reinterpret_cast<uint16_t *>(base);
-    s.cfill = reinterpret_cast<uint16_t *>(base);
+    s.nbr = NBRG ? nbr_scratch + (size_t)blockIdx.x * (size_t)l.cap : reinterpret_cast<uint16_t *>(base);
+    s.cfill = reinterpret_cast<uint16_t *>(base + l.o_cfill);
     s.off = base + l.o_off;
     s.sn = reinterpret_cast<uint32_t *>(base + l.o_sn);
     s.listA = reinterpret_cast<uint16_t *>(base + l.o_listA);
@@ -323,11 +324,11 @@ __device__ __forceinline__ int scan_small(int v, int lane, int nact) {
     return v;
 }
 
-template <int DIM, typename OffT>
+template <int DIM, typename OffT, bool NBRG>
 __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
-    const Smem sm = carve(smem_raw, a.lay);
+    const Smem sm = carve<NBRG>(smem_raw, a.lay, a.nbr_scratch);
     const OffT *off = reinterpret_cast<const OffT *>(sm.off);
     const int N = a.N, T = a.T;
     const double tstop = a.tstop, toff = a.toff;
@@ -628,7 +629,7 @@ __global__ void __launch_bounds__(32) spr_table_dump_kernel(const TrajArgs a, ui
                                                             uint64_t *spos_out, long long *total_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
-    const Smem sm = carve(smem_raw, a.lay);
+    const Smem sm = carve<false>(smem_raw, a.lay, nullptr);
     const PointDev pt = a.pts[slot];
     const int entries = build_table_resampled<DIM, OffT>(sm, a.N, a.L, pt.reach, a.lay.cap, rep, a.pidx[slot],
                                                          a.seed_lo, a.seed_hi, lane);
@@ -814,16 +815,18 @@ __global__ void scatter_idx_kernel(const double *__restrict__ rows, const long l
     }
 }
 
-template <int DIM, typename OffT>
+template <int DIM, typename OffT, bool NBRG>
 cudaError_t set_smem_attr(int bytes) {
     static int configured = -1;
     if (bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<DIM, OffT>,
+        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<DIM, OffT, NBRG>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(spr_table_dump_kernel<DIM, OffT>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        if (e != cudaSuccess) return e;
+        if (!NBRG) {
+            e = cudaFuncSetAttribute(spr_table_dump_kernel<DIM, OffT>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            if (e != cudaSuccess) return e;
+        }
         configured = bytes;
     }
     return cudaSuccess;
@@ -833,17 +836,20 @@ inline int align16(int x) { return (x + 15) & ~15; }
 
 }  // namespace
 
-SmemLayout make_layout(int N, int DIM, int cap) {
+SmemLayout make_layout(int N, int DIM, int cap, bool nbr_global) {
     (void)DIM;
     SmemLayout l;
-    // cfill (u16 per cell, <= 1024 cells) aliases nbr during setup
     if (cap < 1024) cap = 1024;
     cap = (cap + 63) & ~63;
     l.cap = cap;
     l.wide_off = cap > 65535 ? 1 : 0;
+    l.nbr_global = nbr_global ? 1 : 0;
     int o = 0;
-    o += align16(cap * 2);
+    // cfill (u16 per cell, <= min(N,1024) cells, setup only) aliases nbr, or off when nbr is in global memory
+    l.o_cfill = 0;
+    if (!nbr_global) o += align16(cap * 2);
     l.o_off = o;
+    if (nbr_global) l.o_cfill = o;
     o += align16((N + 1) * (l.wide_off ? 4 : 2));
     l.o_region = o;
     // state view: the A list (u16, from the front) and the complex list (u32 pairs, from the back) share
@@ -873,36 +879,42 @@ int max_dynamic_smem(int device) {
     return v;
 }
 
-// (DIM, offset width) -> template instantiation
+// (DIM, offset width, table placement) -> template instantiation
 template <typename F>
-cudaError_t dispatch(int DIM, int wide, F &&f) {
+cudaError_t dispatch(int DIM, int wide, int nbrg, F &&f) {
+    using I3 = std::integral_constant<int, 3>;
+    using I2 = std::integral_constant<int, 2>;
+    using TT = std::true_type;
+    using FF = std::false_type;
     if (DIM == 3) {
-        if (wide) return f(std::integral_constant<int, 3>{}, uint32_t{});
-        return f(std::integral_constant<int, 3>{}, uint16_t{});
+        if (wide) return nbrg ? f(I3{}, uint32_t{}, TT{}) : f(I3{}, uint32_t{}, FF{});
+        return nbrg ? f(I3{}, uint16_t{}, TT{}) : f(I3{}, uint16_t{}, FF{});
     }
-    if (wide) return f(std::integral_constant<int, 2>{}, uint32_t{});
-    return f(std::integral_constant<int, 2>{}, uint16_t{});
+    if (wide) return nbrg ? f(I2{}, uint32_t{}, TT{}) : f(I2{}, uint32_t{}, FF{});
+    return nbrg ? f(I2{}, uint16_t{}, TT{}) : f(I2{}, uint16_t{}, FF{});
 }
 
 cudaError_t launch_traj(const TrajArgs &a, int DIM, int nblocks, cudaStream_t st) {
-    return dispatch(DIM, a.lay.wide_off, [&](auto dim_c, auto off_t) -> cudaError_t {
+    return dispatch(DIM, a.lay.wide_off, a.lay.nbr_global, [&](auto dim_c, auto off_t, auto g_c) -> cudaError_t {
         constexpr int D_ = decltype(dim_c)::value;
         using O_ = decltype(off_t);
-        cudaError_t e = set_smem_attr<D_, O_>(a.lay.total);
+        constexpr bool G_ = decltype(g_c)::value;
+        cudaError_t e = set_smem_attr<D_, O_, G_>(a.lay.total);
         if (e != cudaSuccess) return e;
-        spr_traj_kernel<D_, O_><<<nblocks, 32, a.lay.total, st>>>(a);
+        spr_traj_kernel<D_, O_, G_><<<nblocks, 32, a.lay.total, st>>>(a);
         return cudaGetLastError();
     });
 }
 
 int traj_blocks_per_sm(const SmemLayout &lay, int DIM) {
     int nb = 0;
-    cudaError_t e = dispatch(DIM, lay.wide_off, [&](auto dim_c, auto off_t) -> cudaError_t {
+    cudaError_t e = dispatch(DIM, lay.wide_off, lay.nbr_global, [&](auto dim_c, auto off_t, auto g_c) -> cudaError_t {
         constexpr int D_ = decltype(dim_c)::value;
         using O_ = decltype(off_t);
-        cudaError_t e2 = set_smem_attr<D_, O_>(lay.total);
+        constexpr bool G_ = decltype(g_c)::value;
+        cudaError_t e2 = set_smem_attr<D_, O_, G_>(lay.total);
         if (e2 != cudaSuccess) return e2;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spr_traj_kernel<D_, O_>, 32, lay.total);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spr_traj_kernel<D_, O_, G_>, 32, lay.total);
     });
     return e == cudaSuccess ? nb : 0;
 }
@@ -910,10 +922,10 @@ int traj_blocks_per_sm(const SmemLayout &lay, int DIM) {
 cudaError_t launch_table_dump(const TrajArgs &a, int DIM, uint32_t replicate, int slot, uint32_t *d_off_out,
                               uint16_t *d_nbr_out, uint64_t *d_spos_out, long long *d_total_out,
                               cudaStream_t st) {
-    return dispatch(DIM, a.lay.wide_off, [&](auto dim_c, auto off_t) -> cudaError_t {
+    return dispatch(DIM, a.lay.wide_off, 0, [&](auto dim_c, auto off_t, auto) -> cudaError_t {
         constexpr int D_ = decltype(dim_c)::value;
         using O_ = decltype(off_t);
-        cudaError_t e = set_smem_attr<D_, O_>(a.lay.total);
+        cudaError_t e = set_smem_attr<D_, O_, false>(a.lay.total);
         if (e != cudaSuccess) return e;
         spr_table_dump_kernel<D_, O_><<<1, 32, a.lay.total, st>>>(a, replicate, slot, d_off_out, d_nbr_out,
                                                                  d_spos_out, d_total_out);

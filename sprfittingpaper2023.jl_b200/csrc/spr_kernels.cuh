@@ -24,8 +24,11 @@ struct SmemLayout {
     int o_cstart;  // u16[ncell+1](setup) first sorted index of every cell
     int o_rng;     // 32 x 16 B   block of pre-generated event randoms
     int total;     // bytes of dynamic shared memory
-    int cap;       // nbr capacity (directed entries, u16 each); cfill (setup) aliases nbr
+    int cap;       // nbr capacity (directed entries, u16 each)
     int wide_off;  // OffT = uint32_t when cap > 65535
+    int o_cfill;   // u16[ncell]  (setup) aliases nbr (table in shared memory) or off (table in global memory)
+    int nbr_global;// neighbour table lives in a per-CTA slice of TrajArgs::nbr_scratch (L2-resident)
+                   // instead of shared memory: more trajectories per SM for wide tables
 };
 
 enum { OBS_TOTAL_BOUND = 0, OBS_TOTAL_A = 1, OBS_RAW_BC = 2 };
@@ -50,12 +53,13 @@ struct TrajArgs {
     long long *ovf_list;            // tickets whose neighbour table exceeded `cap`
     unsigned int *ovf_count;
     unsigned int ovf_cap;
+    uint16_t *nbr_scratch;          // [nblocks][lay.cap] when lay.nbr_global
     const uint32_t *g_off;          // fixed-position mode: shared CSR (else nullptr)
     const uint16_t *g_nbr;
     SmemLayout lay;
 };
 
-SmemLayout make_layout(int N, int DIM, int cap);
+SmemLayout make_layout(int N, int DIM, int cap, bool nbr_global = false);
 int max_dynamic_smem(int device);
 // launches the persistent trajectory kernel: `nblocks` single-warp CTAs
 cudaError_t launch_traj(const TrajArgs &a, int DIM, int nblocks, cudaStream_t st);

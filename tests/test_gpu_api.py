@@ -196,14 +196,16 @@ def test_error_behaviour(engine):
     with pytest.raises(sprb200.SprB200Error) as e:
         engine.simulate(ok, [[1, 1, 1, 1]], sprb200.make_run(variance=(0.01, 1, 10)))
     assert e.value.code == _lib.ERR_BAD_ARG
-    # a neighbour table that cannot fit in 227 KB of shared memory: fully connected N = 3000
-    big = sprb200.SimSpec(3000, 3, 50.0, 1.0, 0.5, tsave)
+    # per-particle state that cannot fit in 227 KB of shared memory (10 B per particle + offsets)
+    huge = sprb200.SimSpec(30000, 3, 500.0, 1.0, 0.5, tsave)
     with pytest.raises(sprb200.SprB200Error) as e:
-        engine.simulate(big, [[1, 1, 1, 100.0]], run)
+        engine.simulate(huge, [[1, 1, 1, 1.0]], run)
     assert e.value.code == _lib.ERR_TOO_LARGE
-    # ... while the same N with a small reach is fine
-    out = engine.simulate(big, [[1.0, 1.0, 1.0, 1.0]], run)
-    assert out["n_used"][0] == 2 and out["sum"][0][0] == 0
+    # a fully connected N = 1500 (2.2 M table entries, 4.5 MB) does not fit in shared memory either, but
+    # the table then lives in global memory
+    big = sprb200.SimSpec(1500, 3, 50.0, 0.05, 0.02, tsave)
+    out = engine.simulate(big, [[1.0, 1.0, 1.0, 100.0]], run)
+    assert out["n_used"][0] == 2 and out["sum"][0][0] == 0 and out["sum"][0][1] > 0
 
 
 def test_capacity_overflow_is_rerun(engine, oracle_libs):
