@@ -77,15 +77,25 @@ double spr_mirror_neg_log_u53(uint64_t k) {
 }
 
 /* ---------------------------------------------------------------- waiting time E / a0:
- * correctly rounded float reciprocal + one Newton step in double; plain division outside float range */
-double spr_mirror_event_dt(double E, double a0) {
-    if (a0 < 1e-30 || a0 > 1e30) return E / a0;
-    float af = (float)a0;
-    float rf = 1.0f / af;
-    double r = (double)rf;
-    double y = E * r;
-    double rem = fma(-a0, y, E);
-    return fma(rem, r, y);
+ * exponent-flip seed + four Newton steps + one multiply when the biased exponent of a0 is in
+ * [64, 1984); plain IEEE division otherwise.  Returns t + dt (INFINITY when a0 == 0). */
+double spr_mirror_next_time(double t, double E, double a0) {
+    uint64_t bits;
+    memcpy(&bits, &a0, 8);
+    uint32_t hi = (uint32_t)(bits >> 32);
+    /* device: (uint32)(hiint >> 20) with an arithmetic shift of the signed high word */
+    uint32_t ex = (uint32_t)(((int32_t)hi) >> 20);
+    if ((uint32_t)(ex - 64u) < 1920u) {
+        int64_t rb = (int64_t)0x7FDE6238DA3C2118LL - (int64_t)bits;
+        double r;
+        memcpy(&r, &rb, 8);
+        for (int it = 0; it < 4; it++) {
+            double e = fma(-a0, r, 1.0);
+            r = fma(r, e, r);
+        }
+        return t + E * r;
+    }
+    return a0 > 0.0 ? t + E / a0 : INFINITY;
 }
 
 /* ---------------------------------------------------------------- cell grid */
@@ -294,7 +304,7 @@ int spr_mirror_trajectory(const MirrorSim *sim, double kon_eff, double koff, dou
         const double cB = cA + koff * (double)cntB;
         const double cP = cB + konb * (double)nAB;
         const double a0 = cP + kc * (double)cntC;
-        double tn = a0 > 0.0 ? t + spr_mirror_event_dt(E, a0) : INFINITY;
+        double tn = spr_mirror_next_time(t, E, a0);
         int switched = 0;
         if (on && tn >= toff) { tn = toff; switched = 1; }
         if (tn > tp) {

@@ -21,7 +21,7 @@ if only == "ncusetup":
     run("ncu: setup only reach 15.3", [0.0, 0.1, 1.0, 15.29], 2072)
     sys.exit(0)
 if only == "ncu":
-    run("ncu: pingpong reach35", [1.0, 0.1, 3.0, 35.0], 592, tstop=200.0, toff=100.0, T=201)
+    run("ncu: pingpong reach35", [1.0, 0.1, 3.0, 35.0], 2368, tstop=120.0, toff=60.0, T=121)
     sys.exit(0)
 # setup only: no events (kon = 0)
 for reach in (2.0, 15.29, 24.0, 35.0):

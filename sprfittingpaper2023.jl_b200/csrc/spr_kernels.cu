@@ -100,6 +100,8 @@ struct Smem {
     void *off;
     uint32_t *sn;
     uint16_t *listA, *listB, *pos;
+    uint16_t *h16;     // = listA; listB and pos are h16 + oB, h16 + oP (index offsets in u16 units)
+    int oB, oP;
     uint32_t *listC;   // last word of the array listA lives in: complexes grow downwards from it
     uint64_t *spos;
     uint16_t *cstart;
@@ -117,6 +119,9 @@ __device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &l, 
     s.listA = reinterpret_cast<uint16_t *>(base + l.o_listA);
     s.listB = reinterpret_cast<uint16_t *>(base + l.o_listB);
     s.pos = reinterpret_cast<uint16_t *>(base + l.o_pos);
+    s.h16 = s.listA;
+    s.oB = (l.o_listB - l.o_listA) / 2;
+    s.oP = (l.o_pos - l.o_listA) / 2;
     s.listC = reinterpret_cast<uint32_t *>(base + l.o_listC);
     s.spos = reinterpret_cast<uint64_t *>(base + l.o_spos);
     s.cstart = reinterpret_cast<uint16_t *>(base + l.o_cstart);
@@ -273,11 +278,11 @@ struct NbrRow {
 };
 
 template <typename OffT>
-__device__ __forceinline__ NbrRow load_row(const Smem &sm, const OffT *off, int m, int lane) {
+__device__ __forceinline__ NbrRow load_row(const uint16_t *nbr_lane, const OffT *off, int m, int lane) {
     NbrRow r;
     r.o0 = (int)off[m];
     r.dg = (int)off[m + 1] - r.o0;
-    r.j = lane < r.dg ? (int)sm.nbr[r.o0 + lane] : 0;
+    r.j = lane < r.dg ? (int)nbr_lane[r.o0] : 0;     // nbr_lane = nbr + lane
     return r;
 }
 
@@ -289,7 +294,8 @@ __device__ __forceinline__ void apply_row(const Smem &sm, const NbrRow &r, uint3
         if (PAIR && r.j == other) d += extra;
         sm.sn[r.j] += d;
     }
-    if (r.dg > 32) {
+    if (__builtin_expect(r.dg > 32, 0)) {
+#pragma unroll 1
         for (int q = lane + 32; q < r.dg; q += 32) {
             const int j = sm.nbr[r.o0 + q];
             uint32_t d = delta;
@@ -330,6 +336,7 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
     const int lane = threadIdx.x;
     const Smem sm = carve<NBRG>(smem_raw, a.lay, a.nbr_scratch);
     const OffT *off = reinterpret_cast<const OffT *>(sm.off);
+    const uint16_t *nbr_lane = sm.nbr + lane;
     const int N = a.N, T = a.T;
     const double tstop = a.tstop, toff = a.toff;
     const double *__restrict__ tsave = a.tsave;
@@ -417,7 +424,9 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
             const double cB = __dadd_rn(cA, __dmul_rn(koff, (double)cntB));
             const double cP = __dadd_rn(cB, __dmul_rn(konb, (double)nAB));
             const double a0 = __dadd_rn(cP, __dmul_rn(kc, (double)cntC));
-            double tn = a0 > 0.0 ? __dadd_rn(t, event_dt(E, a0)) : INF;
+            double tn;
+            if (rcp_in_range(a0)) tn = __dadd_rn(t, event_dt_fast(E, a0));
+            else tn = a0 > 0.0 ? __dadd_rn(t, __ddiv_rn(E, a0)) : INF;
 
             if (!(tn < tfast)) {
                 // ---- slow path: antibody bath removed at tstop_AtoB (forward_simulator.jl:174-181,
@@ -462,39 +471,28 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
 
             // ---- channel selection
             const double x = __dmul_rn(__dmul_rn((double)rv.z, 0x1.0p-32), a0);
-            if (x < cA) {
-                // A --> B (forward_simulator.jl:204-224)
-                const int k = (int)__umulhi(rv.w, (uint32_t)cntA);
-                const int m = sm.listA[k];
-                const int lastm = sm.listA[cntA - 1];
-                sm.listA[k] = (uint16_t)lastm;
-                sm.pos[lastm] = (uint16_t)k;
-                --cntA;
-                sm.listB[cntB] = (uint16_t)m;
-                sm.pos[m] = (uint16_t)cntB;
-                ++cntB;
+            if (x < cB) {
+                // A --> B (forward_simulator.jl:204-224) when x < cA, else B --> A (:228-253): the same
+                // code with the two lists swapped
+                const bool ab = x < cA;
+                const int ofrom = ab ? 0 : sm.oB, oto = ab ? sm.oB : 0;
+                const int nfrom = ab ? cntA : cntB, nto = ab ? cntB : cntA;
+                const int k = (int)__umulhi(rv.w, (uint32_t)nfrom);
+                const int m = sm.h16[ofrom + k];
+                const int lastm = sm.h16[ofrom + nfrom - 1];
+                sm.h16[ofrom + k] = (uint16_t)lastm;
+                sm.h16[sm.oP + lastm] = (uint16_t)k;
+                sm.h16[oto + nto] = (uint16_t)m;
+                sm.h16[sm.oP + m] = (uint16_t)nto;
+                const int dAB = ab ? 1 : -1;
+                cntA -= dAB;
+                cntB += dAB;
                 const uint32_t v = sm.sn[m];
-                nAB += sn_nA(v) - sn_nB(v);
-                sm.sn[m] = (v & ~3u) | ST_B;                        // idempotent: every lane stores the same word
-                const NbrRow row = load_row<OffT>(sm, off, m, lane);
-                apply_row<false>(sm, row, (1u << SH_NB) - (1u << SH_NA), 0, 0u, lane);
-                __syncwarp();
-            } else if (x < cB) {
-                // B --> A (:228-253)
-                const int k = (int)__umulhi(rv.w, (uint32_t)cntB);
-                const int m = sm.listB[k];
-                const int lastm = sm.listB[cntB - 1];
-                sm.listB[k] = (uint16_t)lastm;
-                sm.pos[lastm] = (uint16_t)k;
-                --cntB;
-                sm.listA[cntA] = (uint16_t)m;
-                sm.pos[m] = (uint16_t)cntA;
-                ++cntA;
-                const uint32_t v = sm.sn[m];
-                nAB += sn_nB(v) - sn_nA(v);
-                sm.sn[m] = (v & ~3u) | ST_A;
-                const NbrRow row = load_row<OffT>(sm, off, m, lane);
-                apply_row<false>(sm, row, (1u << SH_NA) - (1u << SH_NB), 0, 0u, lane);
+                nAB += dAB * (sn_nA(v) - sn_nB(v));
+                sm.sn[m] = (v & ~3u) | (ab ? ST_B : ST_A);          // idempotent: every lane stores the same word
+                const NbrRow row = load_row<OffT>(nbr_lane, off, m, lane);
+                const uint32_t dlt = (1u << SH_NB) - (1u << SH_NA);
+                apply_row<false>(sm, row, ab ? dlt : 0u - dlt, 0, 0u, lane);
                 __syncwarp();
             } else if (x < cP) {
                 // A + B --> C (:256-289): pair number k of the nAB active pairs, enumerated along the
@@ -515,7 +513,7 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
                         w = (int)((sm.sn[xm] >> sh) & CNT_MASK);
                     }
                     const int incl = scan_small(w, lane, nact);
-                    const int tot = __shfl_sync(FULL, incl, nact - 1);
+                    const int tot = nact > 1 ? __shfl_sync(FULL, incl, nact - 1) : __shfl_sync(FULL, w, 0);
                     if (k < tot) {
                         const uint32_t hit = __ballot_sync(FULL, k < incl);
                         const int Lh = __ffs(hit) - 1;
@@ -566,8 +564,8 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
                     ++cntC;
                 }
                 const uint32_t va = sm.sn[ma], vb = sm.sn[mb];
-                const NbrRow rowa = load_row<OffT>(sm, off, ma, lane);
-                const NbrRow rowb = load_row<OffT>(sm, off, mb, lane);
+                const NbrRow rowa = load_row<OffT>(nbr_lane, off, ma, lane);
+                const NbrRow rowb = load_row<OffT>(nbr_lane, off, mb, lane);
                 nAB -= sn_nB(va) + sn_nA(vb) - 1;
                 __syncwarp();   // every lane has read va, vb before the partner words change
                 // a's neighbours lose an A neighbour, and b (one of them) drops B(2) -> C(0);
@@ -595,8 +593,8 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
                 sm.pos[mb] = (uint16_t)cntB;
                 ++cntB;
                 const uint32_t va = sm.sn[ma], vb = sm.sn[mb];
-                const NbrRow rowa = load_row<OffT>(sm, off, ma, lane);
-                const NbrRow rowb = load_row<OffT>(sm, off, mb, lane);
+                const NbrRow rowa = load_row<OffT>(nbr_lane, off, ma, lane);
+                const NbrRow rowb = load_row<OffT>(nbr_lane, off, mb, lane);
                 nAB += sn_nB(va) + sn_nA(vb) + 1;
                 __syncwarp();
                 // a's neighbours gain an A neighbour, and b becomes B: C(0) -> B(2);
