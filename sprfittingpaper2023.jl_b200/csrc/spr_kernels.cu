@@ -195,73 +195,97 @@ __device__ int build_table_resampled(const Smem &sm, int N, double L, double rea
         }
         __syncwarp();
     }
-    // passes 3 (count) and 4 (fill): one particle per lane.  Candidates come from the 3^DIM cells around
-    // the particle in (dz,dy,dx) order; the three x-cells of a (dz,dy) row are contiguous in the sorted
-    // numbering except across the periodic wrap, so a row is one or two index ranges.  The loop is
-    // flattened over (row, range, candidate) to keep the 32 lanes busy despite unequal cell fillings.
+    // pass 3: the table, one particle per warp iteration.  The candidates of particle i are the
+    // particles of the 3^DIM cells around it in (dz,dy,dx) order; the three x-cells of a (dz,dy) row are
+    // contiguous in the sorted numbering except across the periodic wrap, so they form nr <= 2*3^(DIM-1)
+    // index ranges.  One lane per range computes (first index, length); a warp scan turns the lengths
+    // into positions in the flattened candidate list, the ranges are expanded into a 256-entry window
+    // (it lives in the idle rng block), and all 32 lanes then test consecutive candidates and append
+    // the hits in order with a ballot prefix: no second counting pass and no idle lanes.  Consecutive
+    // particles of the same cell reuse the expanded list.
+    uint16_t *cand = reinterpret_cast<uint16_t *>(sm.rng);
+    constexpr int WIN = 256;
     const int nrow = nc >= 3 ? (DIM == 3 ? 9 : 3) : 1;
-    int total = 0;
+    int running = 0;
+    if (lane == 0) off[0] = 0;
+    int prev_cell = -1, start = 0, len = 0, jb = 0, ctot = 0, mxl = 0, nr = 1;
+    bool cand_ok = false;
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int base = 0; base < N; base += 32) {
-            const int i = base + lane;
-            if (i < N) {
-                const uint64_t ki = sm.spos[i];
-                const int cx = (int)((pos_axis(ki, 0) * (uint32_t)nc) >> POS_BITS);
-                const int cy = (int)((pos_axis(ki, 1) * (uint32_t)nc) >> POS_BITS);
-                const int cz = DIM == 3 ? (int)((pos_axis(ki, 2) * (uint32_t)nc) >> POS_BITS) : 0;
-                int cnt = 0;
-                int wp = pass ? (int)off[i] : 0;
-                int r = 0, h = 0, j = 0, je = 0;
-                for (;;) {
-                    if (j < je) {
-                        if (j != i && within_reach<DIM>(ki, sm.spos[j], r2lat)) {
-                            if (pass) sm.nbr[wp++] = (uint16_t)j;
-                            else ++cnt;
-                        }
-                        ++j;
+    for (int i = 0; i < N; ++i) {
+        const uint64_t ki = sm.spos[i];
+        const int cx = (int)((pos_axis(ki, 0) * (uint32_t)nc) >> POS_BITS);
+        const int cy = (int)((pos_axis(ki, 1) * (uint32_t)nc) >> POS_BITS);
+        const int cz = DIM == 3 ? (int)((pos_axis(ki, 2) * (uint32_t)nc) >> POS_BITS) : 0;
+        const int cell = (cz * nc + cy) * nc + cx;
+        if (cell != prev_cell) {
+            prev_cell = cell;
+            cand_ok = false;
+            const bool edge = nc >= 3 && (cx == 0 || cx == nc - 1);
+            nr = nc < 3 ? 1 : (edge ? 2 * nrow : nrow);
+            len = 0;
+            jb = 0;
+            if (lane < nr) {
+                int ca = 0, cb = 1;
+                if (nc >= 3) {
+                    const int r = edge ? lane >> 1 : lane;
+                    const int half = edge ? lane & 1 : 0;
+                    int yy = cy + (DIM == 3 ? r % 3 : r) - 1;
+                    yy = yy < 0 ? yy + nc : (yy >= nc ? yy - nc : yy);
+                    int zz = 0;
+                    if (DIM == 3) {
+                        zz = cz + r / 3 - 1;
+                        zz = zz < 0 ? zz + nc : (zz >= nc ? zz - nc : zz);
+                    }
+                    const int rb = (zz * nc + yy) * nc;
+                    if (cx == 0) {
+                        if (half == 0) { ca = rb + nc - 1; cb = rb + nc; } else { ca = rb; cb = rb + 2; }
+                    } else if (cx == nc - 1) {
+                        if (half == 0) { ca = rb + nc - 2; cb = rb + nc; } else { ca = rb; cb = rb + 1; }
                     } else {
-                        if (r == nrow) break;
-                        int ca, cb;
-                        if (nc < 3) {
-                            ca = 0; cb = 1; ++r;
-                        } else {
-                            int yy = cy + (DIM == 3 ? r % 3 : r) - 1;
-                            yy = yy < 0 ? yy + nc : (yy >= nc ? yy - nc : yy);
-                            int zz = 0;
-                            if (DIM == 3) {
-                                zz = cz + r / 3 - 1;
-                                zz = zz < 0 ? zz + nc : (zz >= nc ? zz - nc : zz);
-                            }
-                            const int rb = (zz * nc + yy) * nc;
-                            if (cx == 0) {
-                                if (h == 0) { ca = rb + nc - 1; cb = rb + nc; h = 1; }
-                                else { ca = rb; cb = rb + 2; h = 0; ++r; }
-                            } else if (cx == nc - 1) {
-                                if (h == 0) { ca = rb + nc - 2; cb = rb + nc; h = 1; }
-                                else { ca = rb; cb = rb + 1; h = 0; ++r; }
-                            } else {
-                                ca = rb + cx - 1; cb = rb + cx + 2; ++r;
-                            }
-                        }
-                        j = sm.cstart[ca];
-                        je = sm.cstart[cb];
+                        ca = rb + cx - 1; cb = rb + cx + 2;
                     }
                 }
-                if (!pass) off[i] = (OffT)cnt;   // degree < 65536 always (N <= 65535)
+                jb = sm.cstart[ca];
+                len = (int)sm.cstart[cb] - jb;
+            }
+            const int incl = warp_incl_scan(len, lane, 32);
+            start = incl - len;
+            ctot = __shfl_sync(FULL, incl, 31);
+            mxl = __reduce_max_sync(FULL, len);
+        }
+#pragma unroll 1
+        for (int w0 = 0; w0 < ctot; w0 += WIN) {
+            const int wend = min(ctot - w0, WIN);
+            if (nr > 1 && !cand_ok) {
+                __syncwarp();
+#pragma unroll 1
+                for (int tt = 0; tt < mxl; ++tt) {
+                    const int pq = start + tt - w0;
+                    if (tt < len && (unsigned)pq < (unsigned)WIN) cand[pq] = (uint16_t)(jb + tt);
+                }
+                __syncwarp();
+                cand_ok = ctot <= WIN;      // a single window stays valid for the next particles of the cell
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < wend; c0 += 32) {
+                const int f = c0 + lane;
+                int j = 0;
+                bool hit = false;
+                if (f < wend) {
+                    j = nr > 1 ? (int)cand[f] : w0 + f;       // a single range [0, N): the candidate is its own index
+                    hit = j != i && within_reach<DIM>(ki, sm.spos[j], r2lat);
+                }
+                const uint32_t bal = __ballot_sync(FULL, hit);
+                const int nh = __popc(bal);
+                if (running + nh > cap) return -1;
+                if (hit) sm.nbr[running + __popc(bal & lanemask_lt())] = (uint16_t)j;
+                running += nh;
             }
         }
-        __syncwarp();
-        if (!pass) {
-            if (lane == 0) off[N] = 0;
-            __syncwarp();
-            int limit = cap;
-            total = warp_exclusive_scan_inplace<OffT>(off, N + 1, lane, &limit);
-            if (total > cap) return -1;
-            __syncwarp();
-        }
+        if (lane == 0) off[i + 1] = (OffT)running;
     }
-    return total;
+    __syncwarp();
+    return running;
 }
 
 // ------------------------------------------------------------------------------------------------
