@@ -71,6 +71,7 @@ struct sprb200_ctx {
     // the surrogate grids, so the default is 0; SPRB200_NBR_GLOBAL_MIN_CAP overrides (1e9 = always shared).
     long long nbr_global_min_cap = 0;
     size_t nbr_scratch_budget = (size_t)6 << 30;
+    int max_bps = 0;          // SPRB200_MAX_BPS (experiment hook): cap on resident trajectories per SM
 };
 
 namespace {
@@ -350,8 +351,9 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                                     " entries) needs " + std::to_string(lay.total) + " B of shared memory, limit " +
                                     std::to_string(h->smem_optin));
                 }
-                const int bps = traj_blocks_per_sm(lay, DIM);
+                int bps = traj_blocks_per_sm(lay, DIM);
                 if (bps < 1) { free_graphs(); return fail(h, SPRB200_ERR_TOO_LARGE, "trajectory kernel does not fit on an SM"); }
+                if (h->max_bps > 0 && bps > h->max_bps) bps = h->max_bps;
                 const long long ntick = (long long)cw.slots.size() * (rep_hi - rep_lo);
                 long long nblocks = std::min<long long>(ntick, (long long)bps * h->num_sms);
                 size_t off = 0;
@@ -620,6 +622,7 @@ int sprb200_create(int device_ordinal, sprb200_handle *out) {
         const long long v = std::atoll(env);
         if (v >= 0) h->nbr_global_min_cap = v;
     }
+    if (const char *env = std::getenv("SPRB200_MAX_BPS")) h->max_bps = std::atoi(env);
     if (const char *env = std::getenv("SPRB200_CAP_SCALE")) {
         const double v = std::atof(env);
         if (v > 0.0 && v <= 1.0) h->cap_scale = v;
