@@ -53,25 +53,21 @@ struct DevBuf {
 struct sprb200_ctx {
     int device = 0;
     int num_sms = 0;
-    int smem_optin = 0;
+    int smem_optin = 0;      // largest dynamic shared memory of one CTA
+    int smem_per_sm = 0;     // shared memory of one SM (every resident CTA also reserves 1 KB of it)
     cudaStream_t stream[NSTREAM] = {};
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_ready = nullptr, ev_done[NSTREAM] = {};
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::string err;
     // arenas
     DevBuf tsave, pts, pidx, order, curve, curve2, sum, sumsq, nused, nevents, nscanned, nstar, active, counters,
-        ovf, rows, locs, goff, gnbr, misc, table, nbrscratch, nbrscratch2;
+        rows, locs, goff, gnbr, misc, table, arena, desc, defer, tickets, slotrec;
     // stats of the last call
     uint64_t st_traj = 0, st_events = 0, st_launches = 0;
     double st_ms = 0.0;
-    size_t curve_budget = (size_t)8 << 30;
-    double cap_scale = 1.0;   // SPRB200_CAP_SCALE (test hook): shrinks the a-priori table capacity
-    // Tables of at least this many entries live in global memory (L2-resident, one slice per CTA) instead
-    // of shared memory: the extra L2 latency per row is outweighed by 16 instead of 5-14 resident
-    // trajectories per SM.  Measured on B200 (profiles/README.md): global wins for every reach class of
-    // the surrogate grids, so the default is 0; SPRB200_NBR_GLOBAL_MIN_CAP overrides (1e9 = always shared).
-    long long nbr_global_min_cap = 0;
-    size_t nbr_scratch_budget = (size_t)6 << 30;
-    int max_bps = 0;          // SPRB200_MAX_BPS (experiment hook): cap on resident trajectories per SM
+    size_t curve_budget = (size_t)8 << 30;    // SPRB200_CURVE_BYTES: replicate curves resident per batch
+    size_t table_budget = (size_t)16 << 30;   // SPRB200_TABLE_BYTES: neighbour-table arena (K2 -> K1)
+    double est_scale = 1.0;   // SPRB200_CAP_SCALE (test hook): scales the a-priori table size used for chunking
+    int max_warps = 0;        // SPRB200_MAX_WARPS (experiment hook): cap on resident trajectories per SM
 };
 
 namespace {
@@ -134,22 +130,18 @@ int check_points(sprb200_ctx *h, const PointDev *pts, int64_t npts) {
     return SPRB200_OK;
 }
 
-// capacity (directed neighbour entries) that a trajectory at this reach needs with overwhelming
-// probability: mean + 8 sigma of 2 x (pair count); overflowing trajectories are re-run wider.
-int capacity_for(int N, int DIM, double L, double reach, double cap_scale = 1.0) {
+// A-priori size of one neighbour-table record at this reach (mean + 3 sigma of the directed entry
+// count): only used to cut the ticket range into chunks that fit the arena.  K2 allocates the exact
+// size; a trajectory that does not fit is deferred to the next chunk, never dropped.
+size_t record_estimate(int N, int DIM, double L, double reach, double scale) {
     const double PI = 3.14159265358979323846;
     double frac = DIM == 3 ? (4.0 / 3.0) * PI * reach * reach * reach / (L * L * L) : PI * reach * reach / (L * L);
     if (frac > 1.0) frac = 1.0;
     const double E = (double)N * (double)(N - 1) * frac;
-    double cap = E + 8.0 * std::sqrt(2.0 * E) + 64.0;
+    double ent = (E + 3.0 * std::sqrt(2.0 * E) + 32.0) * scale;
     const double maxe = (double)N * (double)(N - 1);
-    if (cap > maxe) cap = maxe;
-    cap *= cap_scale;
-    long long c = (long long)std::ceil(cap);
-    c = (c + 511) / 512 * 512;
-    if (c < 1024) c = 1024;
-    if (c > 0x7fffffffLL) c = 0x7fffffffLL;
-    return (int)c;
+    if (ent > maxe) ent = maxe;
+    return record_bytes(N, (unsigned long long)std::ceil(ent));
 }
 
 // rough SSA event count of one trajectory (only used to start expensive points first)
@@ -175,20 +167,50 @@ struct RunPlan {
     bool raw;              // keep curves (simulate_raw)
 };
 
-struct ClassWork {
-    SmemLayout lay;
-    std::vector<int32_t> slots;   // sorted expensive-first
+// one fixed-position neighbour table (K2b) in record format; the caller owns `rec`
+struct FixedGraph {
+    unsigned char *rec = nullptr;
+    long long entries = 0;
+    unsigned int maxdeg = 0;
 };
 
-// table placement for a class: shared memory if it fits and the table is small, else global memory
-bool choose_layout(const sprb200_ctx *h, int N, int DIM, int cap, SmemLayout *out) {
-    const SmemLayout ls = make_layout(N, DIM, cap, false);
-    const SmemLayout lg = make_layout(N, DIM, cap, true);
-    if (ls.total <= h->smem_optin && (long long)cap < h->nbr_global_min_cap) { *out = ls; return true; }
-    if (lg.total <= h->smem_optin) { *out = lg; return true; }
-    if (ls.total <= h->smem_optin) { *out = ls; return true; }
-    *out = lg;
-    return false;
+// needs sim->initlocs already uploaded to h->locs
+int build_fixed_graph(sprb200_ctx *h, const SprSim *sim, double reach, FixedGraph *g) {
+    const int N = sim->N, DIM = sim->DIM;
+    cudaStream_t s0 = h->stream[0];
+    CUDA_TRY(h, h->goff.ensure(sizeof(uint32_t) * (N + 1)));
+    CUDA_TRY(h, h->misc.ensure(64));
+    CUDA_TRY(h, cudaMemsetAsync(h->misc.p, 0, 64, s0));
+    CUDA_TRY(h, launch_fixed_graph(h->locs.as<double>(), N, DIM, sim->L, reach, h->goff.as<uint32_t>(), nullptr, 0,
+                                   h->misc.as<unsigned long long>(),
+                                   reinterpret_cast<unsigned int *>(h->misc.as<unsigned long long>() + 1), s0));
+    unsigned long long res[2] = {0, 0};
+    CUDA_TRY(h, cudaMemcpyAsync(res, h->misc.p, sizeof(res), cudaMemcpyDeviceToHost, s0));
+    CUDA_TRY(h, cudaStreamSynchronize(s0));
+    h->st_launches += 2;
+    g->entries = (long long)res[0];
+    g->maxdeg = (unsigned int)(res[1] & 0xffffffffu);
+    const size_t bytes = record_bytes(N, (unsigned long long)g->entries);
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(h, SPRB200_ERR_ALLOC, "cudaMalloc(fixed graph record)");
+    }
+    g->rec = static_cast<unsigned char *>(p);
+    uint16_t *nbr = reinterpret_cast<uint16_t *>(g->rec + align16z(sizeof(uint32_t) * (size_t)(N + 1)));
+    cudaError_t e = cudaMemcpyAsync(g->rec, h->goff.p, sizeof(uint32_t) * (N + 1), cudaMemcpyDeviceToDevice, s0);
+    if (e == cudaSuccess)
+        e = launch_fixed_graph(h->locs.as<double>(), N, DIM, sim->L, reach, h->goff.as<uint32_t>(), nbr, g->entries,
+                               nullptr, nullptr, s0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s0);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(g->rec);
+        g->rec = nullptr;
+        return fail(h, SPRB200_ERR_CUDA, std::string("fixed graph fill: ") + cudaGetErrorString(e));
+    }
+    h->st_launches += 1;
+    return SPRB200_OK;
 }
 
 // Simulates `npts` points (already on the host as PointDev + pidx).  On return the device arenas hold
@@ -202,6 +224,7 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
     const SprRun *run = plan.run;
     const int N = sim->N, DIM = sim->DIM, T = sim->T;
     const bool variance = run->term_kind == SPRB200_TERM_VARIANCE;
+    const bool fixedpos = !sim->resample_initlocs;
     const int maxrep = variance ? run->maxsims : run->nsims;
     cudaStream_t s0 = h->stream[0];
 
@@ -210,40 +233,42 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, h->tsave.ensure(sizeof(double) * T));
     CUDA_TRY(h, cudaMemcpyAsync(h->tsave.p, sim->tsave, sizeof(double) * T, cudaMemcpyHostToDevice, s0));
+    CUDA_TRY(h, h->counters.ensure(sizeof(unsigned long long) * CTR_COUNT));
+
+    // ---- K2 (resampled positions) must fit one CTA
+    int k2_ctas = 0;
+    if (!fixedpos) {
+        if (table_smem_bytes(N) > h->smem_optin)
+            return fail(h, SPRB200_ERR_TOO_LARGE, "neighbour-table build for N=" + std::to_string(N) + " needs " +
+                                                      std::to_string(table_smem_bytes(N)) +
+                                                      " B of shared memory, limit " + std::to_string(h->smem_optin));
+        k2_ctas = table_ctas_per_sm(N, DIM);
+        if (k2_ctas < 1) return fail(h, SPRB200_ERR_TOO_LARGE, "neighbour-table kernel does not fit on an SM");
+    }
+    {   // the narrowest trajectory layout must fit one warp's slice
+        TrajLayout probe;
+        if (!make_traj_layout(N, false, false, h->smem_optin, h->smem_per_sm, &probe))
+            return fail(h, SPRB200_ERR_TOO_LARGE, "per-trajectory state for N=" + std::to_string(N) + " needs " +
+                                                      std::to_string(probe.slice) + " B of shared memory, limit " +
+                                                      std::to_string(h->smem_optin));
+    }
 
     // ---- fixed positions: one shared neighbour table per distinct reach (K2b)
-    struct FixedGraph { uint32_t *off; uint16_t *nbr; long long entries; int id; };
     std::map<double, FixedGraph> graphs;
-    std::vector<void *> graph_allocs;
     auto free_graphs = [&]() {
-        for (void *p : graph_allocs) cudaFree(p);
-        graph_allocs.clear();
+        for (auto &kv : graphs)
+            if (kv.second.rec) cudaFree(kv.second.rec);
+        graphs.clear();
     };
-    if (!sim->resample_initlocs) {
+    if (fixedpos) {
         CUDA_TRY(h, h->locs.ensure(sizeof(double) * N * DIM));
         CUDA_TRY(h, cudaMemcpyAsync(h->locs.p, sim->initlocs, sizeof(double) * N * DIM, cudaMemcpyHostToDevice, s0));
-        CUDA_TRY(h, h->misc.ensure(64));
         for (int64_t k = 0; k < npts; ++k) {
             const double reach = pts[k].reach;
             if (graphs.count(reach)) continue;
-            FixedGraph g{nullptr, nullptr, 0, (int)graphs.size() + 1};
-            cudaError_t e = cudaMalloc(&g.off, sizeof(uint32_t) * (N + 1));
-            if (e != cudaSuccess) { free_graphs(); return fail(h, SPRB200_ERR_ALLOC, "cudaMalloc(fixed graph offsets)"); }
-            graph_allocs.push_back(g.off);
-            e = launch_fixed_graph(h->locs.as<double>(), N, DIM, sim->L, reach, g.off, nullptr, 0,
-                                   h->misc.as<unsigned long long>(), s0);
-            unsigned long long total = 0;
-            if (e == cudaSuccess) e = cudaMemcpyAsync(&total, h->misc.p, 8, cudaMemcpyDeviceToHost, s0);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(s0);
-            if (e != cudaSuccess) { free_graphs(); return fail(h, SPRB200_ERR_CUDA, std::string("fixed graph: ") + cudaGetErrorString(e)); }
-            h->st_launches += 2;
-            g.entries = (long long)total;
-            e = cudaMalloc(&g.nbr, sizeof(uint16_t) * std::max<long long>(g.entries, 1));
-            if (e != cudaSuccess) { free_graphs(); return fail(h, SPRB200_ERR_ALLOC, "cudaMalloc(fixed graph entries)"); }
-            graph_allocs.push_back(g.nbr);
-            e = launch_fixed_graph(h->locs.as<double>(), N, DIM, sim->L, reach, g.off, g.nbr, g.entries, nullptr, s0);
-            if (e != cudaSuccess) { free_graphs(); return fail(h, SPRB200_ERR_CUDA, std::string("fixed graph fill: ") + cudaGetErrorString(e)); }
-            h->st_launches += 1;
+            FixedGraph g;
+            const int rc = build_fixed_graph(h, sim, reach, &g);
+            if (rc) { free_graphs(); return rc; }
             graphs[reach] = g;
         }
     }
@@ -269,10 +294,14 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
     CUDA_TRY(h, h->nscanned.ensure(sizeof(int32_t) * PB));
     CUDA_TRY(h, h->nstar.ensure(sizeof(int32_t) * PB));
     CUDA_TRY(h, h->active.ensure(sizeof(int32_t) * PB));
+    if (fixedpos) CUDA_TRY(h, h->slotrec.ensure(sizeof(unsigned long long) * PB));
 
     CUDA_TRY(h, cudaEventRecord(h->ev_begin, s0));
     std::vector<int32_t> h_nstar, h_active, h_order;
-    std::vector<unsigned long long> h_nev;
+    std::vector<unsigned long long> h_nev, h_slotrec;
+    std::vector<size_t> h_est;
+    std::vector<long long> deferred, h_defer;
+    const size_t budget = std::max(h->table_budget, (size_t)1 << 16);
 
     for (int64_t b0 = 0; b0 < npts; b0 += PB) {
         const int64_t nb = std::min<int64_t>(PB, npts - b0);
@@ -285,6 +314,19 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
             CUDA_TRY(h, cudaMemsetAsync(h->nscanned.p, 0, sizeof(int32_t) * nb, s0));
             CUDA_TRY(h, cudaMemsetAsync(h->nstar.p, 0, sizeof(int32_t) * nb, s0));
         }
+        unsigned int fixed_maxdeg = 0;
+        long long fixed_maxent = 0;
+        if (fixedpos) {
+            h_slotrec.resize(nb);
+            for (int64_t k = 0; k < nb; ++k) {
+                const FixedGraph &g = graphs[pts[b0 + k].reach];
+                h_slotrec[k] = (unsigned long long)(uintptr_t)g.rec;
+                fixed_maxdeg = std::max(fixed_maxdeg, g.maxdeg);
+                fixed_maxent = std::max(fixed_maxent, g.entries);
+            }
+            CUDA_TRY(h, cudaMemcpyAsync(h->slotrec.p, h_slotrec.data(), sizeof(unsigned long long) * nb,
+                                        cudaMemcpyHostToDevice, s0));
+        }
         // active slots of this batch (all of them at first)
         h_active.resize(nb);
         for (int64_t k = 0; k < nb; ++k) h_active[k] = (int32_t)k;
@@ -293,166 +335,146 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
         int rep_lo = 0;                                  // relative to replicate_base
         int rep_hi = variance ? run->minsims : run->nsims;
         while (!h_active.empty()) {
-            // ---- partition the active slots into shared-memory capacity classes
-            std::map<std::pair<int, int>, ClassWork> classes;   // key: (capacity, fixed-graph id)
-            for (int32_t sl : h_active) {
-                const PointDev &p = pts[b0 + sl];
-                int cap, gid = 0;
-                if (sim->resample_initlocs) cap = capacity_for(N, DIM, sim->L, p.reach, h->cap_scale);
-                else {
-                    const FixedGraph &g = graphs[p.reach];
-                    cap = (int)std::min<long long>(std::max<long long>((g.entries + 63) / 64 * 64, 64), 0x7fffffff);
-                    gid = g.id;
-                }
-                ClassWork &cw = classes[std::make_pair(cap, gid)];
-                cw.slots.push_back(sl);
-            }
-            // ---- one persistent launch per class, round-robin over the streams
-            const size_t nclass = classes.size();
-            CUDA_TRY(h, h->counters.ensure(sizeof(unsigned long long) * 2 * nclass + 64));
-            CUDA_TRY(h, cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long) * 2 * nclass + 64, s0));
-            const unsigned int ovf_cap = 1u << 16;
-            CUDA_TRY(h, h->ovf.ensure(sizeof(long long) * ovf_cap * nclass));
-            // order arrays for all classes packed into one upload
-            h_order.clear();
-            std::vector<size_t> class_off;
-            // widest tables first: those classes run the fewest trajectories per SM and finish last, the
-            // cheap small-reach classes then fill the SMs as the wide ones drain
-            std::vector<std::pair<const std::pair<int, int>, ClassWork> *> ordered;
-            for (auto &kv : classes) ordered.push_back(&kv);
-            std::reverse(ordered.begin(), ordered.end());
-            for (auto *kvp : ordered) {
-                ClassWork &cw = kvp->second;
+            // ---- work order of this stage: every active slot, expensive points first
+            const int nrep = rep_hi - rep_lo;
+            {
                 std::vector<std::pair<double, int32_t>> keyed;
-                keyed.reserve(cw.slots.size());
-                for (int32_t sl : cw.slots)
+                keyed.reserve(h_active.size());
+                for (int32_t sl : h_active)
                     keyed.emplace_back(-cost_estimate(pts[b0 + sl], N, DIM, sim->L, sim->tstop, sim->tstop_AtoB), sl);
                 std::sort(keyed.begin(), keyed.end());
-                class_off.push_back(h_order.size());
-                for (auto &kk : keyed) h_order.push_back(kk.second);
+                h_order.resize(keyed.size());
+                h_est.resize(keyed.size());
+                for (size_t k = 0; k < keyed.size(); ++k) {
+                    h_order[k] = keyed[k].second;
+                    h_est[k] = fixedpos ? 0 : record_estimate(N, DIM, sim->L, pts[b0 + keyed[k].second].reach, h->est_scale);
+                }
             }
             CUDA_TRY(h, cudaMemcpyAsync(h->order.p, h_order.data(), sizeof(int32_t) * h_order.size(),
                                         cudaMemcpyHostToDevice, s0));
-            CUDA_TRY(h, cudaEventRecord(h->ev_ready, s0));
+            const long long ntick_total = (long long)h_order.size() * nrep;
+            h->st_traj += (uint64_t)ntick_total;
 
-            struct Launched { int cap; size_t ci; SmemLayout lay; TrajArgs args; };
-            std::vector<Launched> launched;
-            struct Prep { int cap; ClassWork *cw; SmemLayout lay; long long nblocks; size_t scratch_off; };
-            std::vector<Prep> preps;
-            size_t scratch_total = 0;
-            for (auto *kvp : ordered) {
-                const int cap = kvp->first.first;
-                ClassWork &cw = kvp->second;
-                SmemLayout lay;
-                if (!choose_layout(h, N, DIM, cap, &lay)) {
-                    free_graphs();
-                    return fail(h, SPRB200_ERR_TOO_LARGE,
-                                "per-trajectory state (N=" + std::to_string(N) + ", table of " + std::to_string(cap) +
-                                    " entries) needs " + std::to_string(lay.total) + " B of shared memory, limit " +
-                                    std::to_string(h->smem_optin));
-                }
-                int bps = traj_blocks_per_sm(lay, DIM);
-                if (bps < 1) { free_graphs(); return fail(h, SPRB200_ERR_TOO_LARGE, "trajectory kernel does not fit on an SM"); }
-                if (h->max_bps > 0 && bps > h->max_bps) bps = h->max_bps;
-                const long long ntick = (long long)cw.slots.size() * (rep_hi - rep_lo);
-                long long nblocks = std::min<long long>(ntick, (long long)bps * h->num_sms);
-                size_t off = 0;
-                if (lay.nbr_global) {
-                    const size_t per = (size_t)lay.cap * sizeof(uint16_t);
-                    const long long fit = (long long)std::max<size_t>(1, h->nbr_scratch_budget / per);
-                    nblocks = std::min(nblocks, fit);
-                    off = scratch_total;
-                    scratch_total += (size_t)nblocks * per;
-                    scratch_total = (scratch_total + 255) & ~(size_t)255;
-                }
-                preps.push_back(Prep{cap, &cw, lay, nblocks, off});
+            if (!fixedpos) {
+                // one arena allocation per stage (growing it later would synchronise the device)
+                size_t total_est = 0;
+                for (size_t k = 0; k < h_est.size() && total_est < budget; ++k) total_est += h_est[k] * (size_t)nrep;
+                total_est += total_est / 64 + ((size_t)1 << 20);
+                CUDA_TRY(h, h->arena.ensure(std::min(total_est, budget)));
             }
-            if (scratch_total) CUDA_TRY(h, h->nbrscratch.ensure(scratch_total));
-            size_t ci = 0;
-            for (auto &pr : preps) {
-                const int cap = pr.cap;
-                ClassWork &cw = *pr.cw;
-                const SmemLayout &lay = pr.lay;
-                TrajArgs a{};
-                a.N = N; a.T = T; a.L = sim->L; a.tstop = sim->tstop; a.toff = sim->tstop_AtoB;
-                a.tsave = h->tsave.as<double>();
-                a.pts = h->pts.as<PointDev>();
-                a.pidx = h->pidx.as<uint32_t>();
-                a.order = h->order.as<int32_t>() + class_off[ci];
-                a.rep0 = rbase + rep_lo; a.nrep = rep_hi - rep_lo; a.repstride = maxrep; a.rep_rowbase = rbase;
-                a.ntickets = (long long)cw.slots.size() * a.nrep;
-                a.ticket_list = nullptr;
-                a.seed_lo = (uint32_t)(run->seed & 0xffffffffu); a.seed_hi = (uint32_t)(run->seed >> 32);
-                a.ticket_ctr = h->counters.as<unsigned long long>() + 2 * ci;
-                a.curve = h->curve.as<uint16_t>();
-                a.curve2 = planes == 2 ? h->curve2.as<uint16_t>() : nullptr;
-                a.nevents = h->nevents.as<unsigned long long>();
-                a.observable = plan.observable;
-                a.ovf_list = h->ovf.as<long long>() + (size_t)ovf_cap * ci;
-                a.ovf_count = reinterpret_cast<unsigned int *>(h->counters.as<unsigned long long>() + 2 * ci + 1);
-                a.ovf_cap = ovf_cap;
-                a.nbr_scratch = lay.nbr_global ? reinterpret_cast<uint16_t *>(h->nbrscratch.as<unsigned char>() + pr.scratch_off) : nullptr;
-                if (!sim->resample_initlocs) {
-                    const FixedGraph &g = graphs[pts[b0 + cw.slots[0]].reach];
-                    a.g_off = g.off; a.g_nbr = g.nbr;
-                }
-                a.lay = lay;
-                cudaStream_t st = h->stream[ci % NSTREAM];
-                if (st != s0) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_ready, 0));
-                CUDA_TRY(h, launch_traj(a, DIM, (int)pr.nblocks, st));
-                h->st_launches += 1;
-                h->st_traj += (uint64_t)a.ntickets;
-                launched.push_back(Launched{cap, ci, lay, a});
-                ++ci;
-            }
-            for (int s = 1; s < NSTREAM; ++s) {
-                CUDA_TRY(h, cudaEventRecord(h->ev_done[s], h->stream[s]));
-                CUDA_TRY(h, cudaStreamWaitEvent(s0, h->ev_done[s], 0));
-            }
-            // ---- capacity overflows: re-run those tickets with a wider table
-            std::vector<unsigned long long> h_cnt(2 * nclass);
-            CUDA_TRY(h, cudaMemcpyAsync(h_cnt.data(), h->counters.p, sizeof(unsigned long long) * 2 * nclass,
-                                        cudaMemcpyDeviceToHost, s0));
-            CUDA_TRY(h, cudaStreamSynchronize(s0));
-            for (auto &lc : launched) {
-                unsigned int novf = (unsigned int)(h_cnt[2 * lc.ci + 1] & 0xffffffffu);
-                int cap = lc.cap;
-                while (novf > 0) {
-                    if (novf > ovf_cap) { free_graphs(); return fail(h, SPRB200_ERR_INTERNAL, "too many capacity overflows"); }
-                    const long long maxe = (long long)N * (N - 1);
-                    if (cap >= maxe) { free_graphs(); return fail(h, SPRB200_ERR_INTERNAL, "overflow at full capacity"); }
-                    cap = (int)std::min<long long>(maxe + 64, (long long)cap + cap / 4 + 512);
-                    SmemLayout lay;
-                    if (!choose_layout(h, N, DIM, cap, &lay)) {
-                        free_graphs();
-                        return fail(h, SPRB200_ERR_TOO_LARGE, "per-trajectory state does not fit in shared memory after overflow");
+            // ---- chunks of tickets whose tables fit the arena: K2 builds the tables, K1 runs the trajectories
+            long long tk = 0;
+            deferred.clear();
+            while (tk < ntick_total || !deferred.empty()) {
+                long long n = 0;
+                const long long tk0 = tk;
+                const bool explicit_list = !deferred.empty();
+                size_t want = 0;                 // arena bytes this chunk is expected to need
+                if (explicit_list) {
+                    n = (long long)deferred.size();
+                    CUDA_TRY(h, h->tickets.ensure(sizeof(long long) * deferred.size()));
+                    CUDA_TRY(h, cudaMemcpyAsync(h->tickets.p, deferred.data(), sizeof(long long) * deferred.size(),
+                                                cudaMemcpyHostToDevice, s0));
+                    for (long long t : deferred) want += 2 * h_est[(size_t)(t / nrep)] + 4096;
+                    want = std::max(want, record_bytes(N, (unsigned long long)N * (unsigned long long)(N - 1)));
+                } else if (fixedpos) {
+                    n = ntick_total;
+                    tk = ntick_total;
+                } else {
+                    long long tk1 = tk;
+                    while (tk1 < ntick_total) {
+                        const size_t eb = std::max<size_t>(h_est[(size_t)(tk1 / nrep)], 16);
+                        const long long room = (long long)((budget > want ? budget - want : 0) / eb);
+                        const long long take = std::min<long long>(nrep - tk1 % nrep, room);
+                        if (take <= 0) break;
+                        tk1 += take;
+                        want += (size_t)take * eb;
                     }
-                    // move the overflow list aside (misc) and reuse the class's counters
-                    CUDA_TRY(h, h->misc.ensure(sizeof(long long) * novf + 64));
-                    CUDA_TRY(h, cudaMemcpyAsync(h->misc.p, lc.args.ovf_list, sizeof(long long) * novf,
-                                                cudaMemcpyDeviceToDevice, s0));
-                    CUDA_TRY(h, cudaMemsetAsync(lc.args.ticket_ctr, 0, 2 * sizeof(unsigned long long), s0));
-                    TrajArgs a = lc.args;
-                    a.lay = lay;
-                    a.ticket_list = h->misc.as<long long>();
-                    a.ntickets = novf;
-                    const int bps = traj_blocks_per_sm(lay, DIM);
-                    if (bps < 1) { free_graphs(); return fail(h, SPRB200_ERR_TOO_LARGE, "trajectory kernel does not fit on an SM"); }
-                    long long nblk = std::min<long long>(novf, (long long)bps * h->num_sms);
-                    if (lay.nbr_global) {
-                        const size_t per = (size_t)lay.cap * sizeof(uint16_t);
-                        nblk = std::min<long long>(nblk, (long long)std::max<size_t>(1, h->nbr_scratch_budget / per));
-                        CUDA_TRY(h, h->nbrscratch2.ensure((size_t)nblk * per));
-                        a.nbr_scratch = h->nbrscratch2.as<uint16_t>();
-                    } else
-                        a.nbr_scratch = nullptr;
-                    CUDA_TRY(h, launch_traj(a, DIM, (int)nblk, s0));
-                    h->st_launches += 1;
-                    unsigned long long cnt2[2] = {0, 0};
-                    CUDA_TRY(h, cudaMemcpyAsync(cnt2, lc.args.ticket_ctr, sizeof(cnt2), cudaMemcpyDeviceToHost, s0));
-                    CUDA_TRY(h, cudaStreamSynchronize(s0));
-                    novf = (unsigned int)(cnt2[1] & 0xffffffffu);
+                    if (tk1 == tk) { tk1 = tk + 1; want = budget; }   // a single record beyond the estimate: K2 decides
+                    n = tk1 - tk;
+                    tk = tk1;
                 }
+                CUDA_TRY(h, cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long) * CTR_COUNT, s0));
+                unsigned long long ctr[CTR_COUNT] = {};
+                if (!fixedpos) {
+                    want = std::min(want, budget);
+                    CUDA_TRY(h, h->arena.ensure(want));
+                    CUDA_TRY(h, h->desc.ensure(sizeof(unsigned long long) * (size_t)n));
+                    CUDA_TRY(h, h->defer.ensure(sizeof(long long) * (size_t)n));
+                    TableArgs ta{};
+                    ta.N = N; ta.L = sim->L;
+                    ta.pts = h->pts.as<PointDev>(); ta.pidx = h->pidx.as<uint32_t>(); ta.order = h->order.as<int32_t>();
+                    ta.tk0 = tk0; ta.ntickets = n;
+                    ta.ticket_list = explicit_list ? h->tickets.as<long long>() : nullptr;
+                    ta.rep0 = rbase + rep_lo; ta.nrep = nrep;
+                    ta.seed_lo = (uint32_t)(run->seed & 0xffffffffu); ta.seed_hi = (uint32_t)(run->seed >> 32);
+                    ta.ctr = h->counters.as<unsigned long long>();
+                    ta.arena = h->arena.as<unsigned char>();
+                    ta.arena_bytes = std::min<unsigned long long>(h->arena.cap, budget);
+                    ta.desc = h->desc.as<unsigned long long>();
+                    ta.defer_list = h->defer.as<long long>();
+                    ta.spos_out = nullptr;
+                    const long long nblk = std::min<long long>(n, (long long)k2_ctas * h->num_sms);
+                    CUDA_TRY(h, launch_table(ta, DIM, (int)nblk, s0));
+                    h->st_launches += 1;
+                    CUDA_TRY(h, cudaMemcpyAsync(ctr, h->counters.p, sizeof(ctr), cudaMemcpyDeviceToHost, s0));
+                    CUDA_TRY(h, cudaStreamSynchronize(s0));
+                } else {
+                    ctr[CTR_MAX_DEGREE] = fixed_maxdeg;
+                    ctr[CTR_MAX_ENTRIES] = (unsigned long long)fixed_maxent;
+                }
+                const long long ndefer = (long long)ctr[CTR_NDEFER];
+                if (ndefer > 0) {
+                    if (explicit_list && ndefer >= n) {
+                        free_graphs();
+                        return fail(h, SPRB200_ERR_TOO_LARGE, "a neighbour table does not fit the table arena (" +
+                                                                  std::to_string(budget) + " B; SPRB200_TABLE_BYTES)");
+                    }
+                    h_defer.resize((size_t)ndefer);
+                    CUDA_TRY(h, cudaMemcpyAsync(h_defer.data(), h->defer.p, sizeof(long long) * (size_t)ndefer,
+                                                cudaMemcpyDeviceToHost, s0));
+                    CUDA_TRY(h, cudaStreamSynchronize(s0));
+                }
+                if (ndefer < n) {
+                    TrajLayout lay;
+                    const bool wide_sn = ctr[CTR_MAX_DEGREE] > 127ULL, wide_off = ctr[CTR_MAX_ENTRIES] > 65535ULL;
+                    if (!make_traj_layout(N, wide_sn, wide_off, h->smem_optin, h->smem_per_sm, &lay)) {
+                        free_graphs();
+                        return fail(h, SPRB200_ERR_TOO_LARGE,
+                                    "per-trajectory state (N=" + std::to_string(N) + ", max degree " +
+                                        std::to_string(ctr[CTR_MAX_DEGREE]) + ", " + std::to_string(ctr[CTR_MAX_ENTRIES]) +
+                                        " table entries) needs " + std::to_string(lay.slice) +
+                                        " B of shared memory, limit " + std::to_string(h->smem_optin));
+                    }
+                    if (h->max_warps > 0 && lay.cta_per_sm * lay.wpc > h->max_warps) {
+                        if (h->max_warps < lay.wpc) lay.wpc = h->max_warps;
+                        lay.cta_per_sm = std::max(1, h->max_warps / lay.wpc);
+                    }
+                    TrajArgs a{};
+                    a.N = N; a.T = T; a.tstop = sim->tstop; a.toff = sim->tstop_AtoB;
+                    a.tsave = h->tsave.as<double>();
+                    a.pts = h->pts.as<PointDev>(); a.pidx = h->pidx.as<uint32_t>(); a.order = h->order.as<int32_t>();
+                    a.tk0 = tk0; a.ntickets = n;
+                    a.ticket_list = explicit_list ? h->tickets.as<long long>() : nullptr;
+                    a.rep0 = rbase + rep_lo; a.nrep = nrep; a.repstride = maxrep; a.rep_rowbase = rbase;
+                    a.seed_lo = (uint32_t)(run->seed & 0xffffffffu); a.seed_hi = (uint32_t)(run->seed >> 32);
+                    a.ctr = h->counters.as<unsigned long long>();
+                    a.desc = fixedpos ? nullptr : h->desc.as<unsigned long long>();
+                    a.slot_rec = fixedpos ? h->slotrec.as<unsigned long long>() : nullptr;
+                    a.curve = h->curve.as<uint16_t>();
+                    a.curve2 = planes == 2 ? h->curve2.as<uint16_t>() : nullptr;
+                    a.nevents = h->nevents.as<unsigned long long>();
+                    a.observable = plan.observable;
+                    a.lay = lay;
+                    const long long nblk = std::min<long long>((n + lay.wpc - 1) / lay.wpc,
+                                                               (long long)lay.cta_per_sm * h->num_sms);
+                    CUDA_TRY(h, launch_traj(a, (int)nblk, s0));
+                    h->st_launches += 1;
+                    // the arena, descriptors and ticket list are reused by the next chunk: stream order keeps
+                    // this launch ahead of the next K2
+                }
+                if (ndefer > 0) deferred.assign(h_defer.begin(), h_defer.begin() + ndefer);
+                else deferred.clear();
             }
             // ---- K3
             if (!variance) {
@@ -606,26 +628,25 @@ int sprb200_create(int device_ordinal, sprb200_handle *out) {
     h->device = device_ordinal;
     h->num_sms = prop.multiProcessorCount;
     if (cudaSetDevice(device_ordinal) != cudaSuccess) { delete h; return fail(nullptr, SPRB200_ERR_CUDA, "cudaSetDevice"); }
-    h->smem_optin = max_dynamic_smem(device_ordinal);
+    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     for (int s = 0; s < NSTREAM; ++s) {
         if (cudaStreamCreateWithFlags(&h->stream[s], cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, SPRB200_ERR_CUDA, "cudaStreamCreate"); }
-        cudaEventCreateWithFlags(&h->ev_done[s], cudaEventDisableTiming);
     }
     cudaEventCreate(&h->ev_begin);
     cudaEventCreate(&h->ev_end);
-    cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming);
     if (const char *env = std::getenv("SPRB200_CURVE_BYTES")) {
         const long long v = std::atoll(env);
         if (v > 0) h->curve_budget = (size_t)v;
     }
-    if (const char *env = std::getenv("SPRB200_NBR_GLOBAL_MIN_CAP")) {
+    if (const char *env = std::getenv("SPRB200_TABLE_BYTES")) {
         const long long v = std::atoll(env);
-        if (v >= 0) h->nbr_global_min_cap = v;
+        if (v > 0) h->table_budget = (size_t)v;
     }
-    if (const char *env = std::getenv("SPRB200_MAX_BPS")) h->max_bps = std::atoi(env);
+    if (const char *env = std::getenv("SPRB200_MAX_WARPS")) h->max_warps = std::atoi(env);
     if (const char *env = std::getenv("SPRB200_CAP_SCALE")) {
         const double v = std::atof(env);
-        if (v > 0.0 && v <= 1.0) h->cap_scale = v;
+        if (v > 0.0 && v <= 1.0) h->est_scale = v;
     }
     *out = h;
     return SPRB200_OK;
@@ -638,16 +659,14 @@ void sprb200_destroy(sprb200_handle h) {
         if (h->stream[s]) cudaStreamSynchronize(h->stream[s]);
     }
     DevBuf *bufs[] = {&h->tsave, &h->pts, &h->pidx, &h->order, &h->curve, &h->curve2, &h->sum, &h->sumsq, &h->nused,
-                      &h->nevents, &h->nscanned, &h->nstar, &h->active, &h->counters, &h->ovf, &h->rows, &h->locs,
-                      &h->goff, &h->gnbr, &h->misc, &h->table, &h->nbrscratch, &h->nbrscratch2};
+                      &h->nevents, &h->nscanned, &h->nstar, &h->active, &h->counters, &h->rows, &h->locs,
+                      &h->goff, &h->gnbr, &h->misc, &h->table, &h->arena, &h->desc, &h->defer, &h->tickets, &h->slotrec};
     for (DevBuf *b : bufs) b->release();
     for (int s = 0; s < NSTREAM; ++s) {
-        if (h->ev_done[s]) cudaEventDestroy(h->ev_done[s]);
         if (h->stream[s]) cudaStreamDestroy(h->stream[s]);
     }
     if (h->ev_begin) cudaEventDestroy(h->ev_begin);
     if (h->ev_end) cudaEventDestroy(h->ev_end);
-    if (h->ev_ready) cudaEventDestroy(h->ev_ready);
     delete h;
 }
 
@@ -762,59 +781,63 @@ int64_t sprb200_neighbor_table(sprb200_handle h, const SprSim *sim, double reach
     std::vector<uint32_t> off(N + 1);
     std::vector<uint16_t> nbr;
     long long total = 0;
+    const size_t o_nbr = align16z(sizeof(uint32_t) * (size_t)(N + 1));
     if (!sim->resample_initlocs) {
         CUDA_TRY(h, h->locs.ensure(sizeof(double) * N * DIM));
         CUDA_TRY(h, cudaMemcpyAsync(h->locs.p, sim->initlocs, sizeof(double) * N * DIM, cudaMemcpyHostToDevice, s0));
-        CUDA_TRY(h, h->goff.ensure(sizeof(uint32_t) * (N + 1)));
-        CUDA_TRY(h, h->misc.ensure(64));
-        CUDA_TRY(h, launch_fixed_graph(h->locs.as<double>(), N, DIM, sim->L, reach, h->goff.as<uint32_t>(), nullptr, 0,
-                                       h->misc.as<unsigned long long>(), s0));
-        unsigned long long tot = 0;
-        CUDA_TRY(h, cudaMemcpyAsync(&tot, h->misc.p, 8, cudaMemcpyDeviceToHost, s0));
-        CUDA_TRY(h, cudaStreamSynchronize(s0));
-        total = (long long)tot;
-        CUDA_TRY(h, h->gnbr.ensure(sizeof(uint16_t) * std::max<long long>(total, 1)));
-        CUDA_TRY(h, launch_fixed_graph(h->locs.as<double>(), N, DIM, sim->L, reach, h->goff.as<uint32_t>(),
-                                       h->gnbr.as<uint16_t>(), total, nullptr, s0));
+        FixedGraph g;
+        rc = build_fixed_graph(h, sim, reach, &g);
+        if (rc) return rc;
+        total = g.entries;
         nbr.resize((size_t)std::max<long long>(total, 1));
-        CUDA_TRY(h, cudaMemcpyAsync(off.data(), h->goff.p, sizeof(uint32_t) * (N + 1), cudaMemcpyDeviceToHost, s0));
-        CUDA_TRY(h, cudaMemcpyAsync(nbr.data(), h->gnbr.p, sizeof(uint16_t) * total, cudaMemcpyDeviceToHost, s0));
-        CUDA_TRY(h, cudaStreamSynchronize(s0));
+        cudaError_t e = cudaMemcpyAsync(off.data(), g.rec, sizeof(uint32_t) * (N + 1), cudaMemcpyDeviceToHost, s0);
+        if (e == cudaSuccess && total > 0)
+            e = cudaMemcpyAsync(nbr.data(), g.rec + o_nbr, sizeof(uint16_t) * total, cudaMemcpyDeviceToHost, s0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s0);
+        cudaFree(g.rec);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(h, SPRB200_ERR_CUDA, std::string("fixed graph copy: ") + cudaGetErrorString(e)); }
         if (positions_out) std::memcpy(positions_out, sim->initlocs, sizeof(double) * N * DIM);
     } else {
         if (param_index > 0xffffffffULL) return fail(h, SPRB200_ERR_BAD_ARG, "parameter index exceeds 2^32");
-        int cap = capacity_for(N, DIM, sim->L, reach);
-        for (;;) {
-            SmemLayout lay = make_layout(N, DIM, cap);
-            if (lay.total > h->smem_optin) return fail(h, SPRB200_ERR_TOO_LARGE, "neighbour table does not fit in shared memory");
-            PointDev p{0, 0, 0, reach};
-            uint32_t pi = (uint32_t)param_index;
-            CUDA_TRY(h, h->pts.ensure(sizeof(PointDev)));
-            CUDA_TRY(h, h->pidx.ensure(sizeof(uint32_t)));
-            CUDA_TRY(h, cudaMemcpyAsync(h->pts.p, &p, sizeof(p), cudaMemcpyHostToDevice, s0));
-            CUDA_TRY(h, cudaMemcpyAsync(h->pidx.p, &pi, sizeof(pi), cudaMemcpyHostToDevice, s0));
-            CUDA_TRY(h, h->goff.ensure(sizeof(uint32_t) * (N + 1)));
-            CUDA_TRY(h, h->gnbr.ensure(sizeof(uint16_t) * (size_t)lay.cap));
-            CUDA_TRY(h, h->locs.ensure(sizeof(uint64_t) * N + sizeof(double) * N * DIM));
-            CUDA_TRY(h, h->misc.ensure(64));
-            TrajArgs a{};
-            a.N = N; a.T = sim->T; a.L = sim->L;
-            a.pts = h->pts.as<PointDev>(); a.pidx = h->pidx.as<uint32_t>();
-            a.seed_lo = (uint32_t)(seed & 0xffffffffu); a.seed_hi = (uint32_t)(seed >> 32);
-            a.lay = lay;
-            CUDA_TRY(h, launch_table_dump(a, DIM, replicate, 0, h->goff.as<uint32_t>(), h->gnbr.as<uint16_t>(),
-                                          h->locs.as<uint64_t>(), h->misc.as<long long>(), s0));
-            CUDA_TRY(h, cudaMemcpyAsync(&total, h->misc.p, 8, cudaMemcpyDeviceToHost, s0));
-            CUDA_TRY(h, cudaStreamSynchronize(s0));
-            if (total >= 0) break;
-            const long long maxe = (long long)N * (N - 1);
-            if (cap >= maxe) return fail(h, SPRB200_ERR_INTERNAL, "overflow at full capacity");
-            cap = (int)std::min<long long>(maxe + 64, (long long)cap + cap / 4 + 512);
-        }
+        if (table_smem_bytes(N) > h->smem_optin || table_ctas_per_sm(N, DIM) < 1)
+            return fail(h, SPRB200_ERR_TOO_LARGE, "neighbour-table build does not fit in shared memory");
+        PointDev p{0, 0, 0, reach};
+        const uint32_t pi = (uint32_t)param_index;
+        const int32_t ord = 0;
+        const size_t recmax = record_bytes(N, (unsigned long long)N * (unsigned long long)(N - 1));
+        CUDA_TRY(h, h->pts.ensure(sizeof(PointDev)));
+        CUDA_TRY(h, h->pidx.ensure(sizeof(uint32_t)));
+        CUDA_TRY(h, h->order.ensure(sizeof(int32_t)));
+        CUDA_TRY(h, h->counters.ensure(sizeof(unsigned long long) * CTR_COUNT));
+        CUDA_TRY(h, h->arena.ensure(recmax));
+        CUDA_TRY(h, h->desc.ensure(sizeof(unsigned long long)));
+        CUDA_TRY(h, h->defer.ensure(sizeof(long long)));
+        CUDA_TRY(h, h->locs.ensure(sizeof(uint64_t) * N + sizeof(double) * N * DIM));
+        CUDA_TRY(h, cudaMemcpyAsync(h->pts.p, &p, sizeof(p), cudaMemcpyHostToDevice, s0));
+        CUDA_TRY(h, cudaMemcpyAsync(h->pidx.p, &pi, sizeof(pi), cudaMemcpyHostToDevice, s0));
+        CUDA_TRY(h, cudaMemcpyAsync(h->order.p, &ord, sizeof(ord), cudaMemcpyHostToDevice, s0));
+        CUDA_TRY(h, cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long) * CTR_COUNT, s0));
+        TableArgs ta{};
+        ta.N = N; ta.L = sim->L;
+        ta.pts = h->pts.as<PointDev>(); ta.pidx = h->pidx.as<uint32_t>(); ta.order = h->order.as<int32_t>();
+        ta.tk0 = 0; ta.ntickets = 1; ta.ticket_list = nullptr;
+        ta.rep0 = (int)replicate; ta.nrep = 1;
+        ta.seed_lo = (uint32_t)(seed & 0xffffffffu); ta.seed_hi = (uint32_t)(seed >> 32);
+        ta.ctr = h->counters.as<unsigned long long>();
+        ta.arena = h->arena.as<unsigned char>(); ta.arena_bytes = h->arena.cap;
+        ta.desc = h->desc.as<unsigned long long>(); ta.defer_list = h->defer.as<long long>();
+        ta.spos_out = h->locs.as<uint64_t>();
+        CUDA_TRY(h, launch_table(ta, DIM, 1, s0));
+        unsigned long long ctr[CTR_COUNT] = {};
+        CUDA_TRY(h, cudaMemcpyAsync(ctr, h->counters.p, sizeof(ctr), cudaMemcpyDeviceToHost, s0));
+        CUDA_TRY(h, cudaStreamSynchronize(s0));
+        if (ctr[CTR_NDEFER] != 0) return fail(h, SPRB200_ERR_INTERNAL, "table did not fit a full-size arena");
+        total = (long long)ctr[CTR_MAX_ENTRIES];
         nbr.resize((size_t)std::max<long long>(total, 1));
         std::vector<uint64_t> spos((size_t)N);
-        CUDA_TRY(h, cudaMemcpyAsync(off.data(), h->goff.p, sizeof(uint32_t) * (N + 1), cudaMemcpyDeviceToHost, s0));
-        CUDA_TRY(h, cudaMemcpyAsync(nbr.data(), h->gnbr.p, sizeof(uint16_t) * total, cudaMemcpyDeviceToHost, s0));
+        CUDA_TRY(h, cudaMemcpyAsync(off.data(), h->arena.p, sizeof(uint32_t) * (N + 1), cudaMemcpyDeviceToHost, s0));
+        if (total > 0)
+            CUDA_TRY(h, cudaMemcpyAsync(nbr.data(), h->arena.as<unsigned char>() + o_nbr, sizeof(uint16_t) * total, cudaMemcpyDeviceToHost, s0));
         CUDA_TRY(h, cudaMemcpyAsync(spos.data(), h->locs.p, sizeof(uint64_t) * N, cudaMemcpyDeviceToHost, s0));
         CUDA_TRY(h, cudaStreamSynchronize(s0));
         if (positions_out) {

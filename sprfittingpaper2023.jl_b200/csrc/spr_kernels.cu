@@ -1,13 +1,15 @@
 // spr_kernels.cu -- hand-written sm_100a kernels for the SSA ensemble (DESIGN.md sections 3-5).
 //
-// K1  spr_traj_kernel      one trajectory per warp (one single-warp CTA), persistent CTAs pulling
-//                          (parameter point, replicate) tickets from a global counter.  Replaces the
-//                          replicate loop + event loop of run_spr_sim!
-//                          (/root/reference/src/forward_simulator.jl:129-361).
-// K2  build_table_*        neighbour table within `reach` on the periodic box from a cell list, in
-//                          the prologue of K1; replaces setup_spr_sim! (forward_simulator.jl:37-89).
-// K2b fixed_graph_*        the same table for user-supplied FP64 positions (resample_initlocs =
-//                          false), built once per call with the reference's periodic_dist_sq (:1-8).
+// K2  spr_table_kernel     neighbour table within `reach` on the periodic box from a cell list: one
+//                          256-thread CTA per trajectory (one thread per particle), persistent CTAs
+//                          pulling tickets from a global counter, exactly-sized records bump-allocated
+//                          in an HBM arena.  Replaces setup_spr_sim!
+//                          (/root/reference/src/forward_simulator.jl:37-89).
+// K1  spr_traj_kernel      one trajectory per warp, up to 25 warps resident per SM (9 bytes of shared
+//                          memory per particle), persistent, same ticket scheme.  Replaces the
+//                          replicate loop + event loop of run_spr_sim! (forward_simulator.jl:129-361).
+// K2b fixed_graph_*        the table for user-supplied FP64 positions (resample_initlocs = false),
+//                          built once per call with the reference's periodic_dist_sq (:1-8).
 // K3  reduce_fixed / variance_scan   replicate reduction and the VarianceTerminator's sequential
 //                          stopping rule (/root/reference/src/callbacks.jl:23-33, 204-217).
 // K4  means / scatter      mean curves in slice order and the [P][T] -> [T][P] permutation into the
@@ -15,7 +17,7 @@
 //
 // Nothing here is a dense contraction: no tensor cores.  The trajectory is a dependent chain of
 // shared-memory reads/writes, shuffles and ALU ops; throughput comes from keeping as many
-// trajectories resident per SM as shared memory allows.
+// trajectories resident per SM as shared memory and registers allow.
 #include "spr_device.cuh"
 #include "spr_kernels.cuh"
 #include <type_traits>
@@ -32,40 +34,6 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     return m;
 }
 
-template <int DIM>
-__device__ __forceinline__ uint64_t gen_position(uint32_t i, uint32_t rep, uint32_t pidx, uint32_t k0, uint32_t k1) {
-    const u32x4 r = philox4x32_10(i, STREAM_POSITIONS, rep, pidx, k0, k1);
-    uint64_t p = (uint64_t)(r.x >> (32 - POS_BITS)) | ((uint64_t)(r.y >> (32 - POS_BITS)) << POS_BITS);
-    if (DIM == 3) p |= (uint64_t)(r.z >> (32 - POS_BITS)) << (2 * POS_BITS);
-    return p;
-}
-
-__device__ __forceinline__ uint32_t pos_axis(uint64_t p, int d) { return (uint32_t)(p >> (d * POS_BITS)) & POS_MASK; }
-
-template <int DIM>
-__device__ __forceinline__ uint32_t cell_of(uint64_t p, uint32_t nc) {
-    uint32_t c = 0;
-#pragma unroll
-    for (int d = DIM - 1; d >= 0; --d) c = c * nc + ((pos_axis(p, d) * nc) >> POS_BITS);
-    return c;
-}
-
-// Squared min-image distance in lattice units, exact in 64-bit integers (each axis < 2^20, so the sum
-// is < 2^42), compared with r2lat = floor(reach^2 / (L 2^-21)^2): the reference's test
-// periodic_dist_sq <= reach^2 (forward_simulator.jl:1-8, 54-55) evaluated without rounding on the lattice.
-template <int DIM>
-__device__ __forceinline__ bool within_reach(uint64_t a, uint64_t b, unsigned long long r2lat) {
-    unsigned long long acc = 0;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-        const uint32_t df = (pos_axis(a, d) - pos_axis(b, d)) & POS_MASK;
-        const uint32_t nd = (0u - df) & POS_MASK;
-        const uint32_t m = df < nd ? df : nd;
-        acc += (unsigned long long)m * m;
-    }
-    return acc <= r2lat;
-}
-
 // r2lat of the specification: floor(reach^2 / scale^2) with scale = L 2^-21, clamped to 2^62
 __host__ __device__ inline unsigned long long reach2_lattice(double L, double reach) {
     const double scale = L * 0x1.0p-21;
@@ -74,224 +42,247 @@ __host__ __device__ inline unsigned long long reach2_lattice(double L, double re
     return (unsigned long long)q;                        // truncation == floor for q >= 0
 }
 
-// in-place exclusive prefix sum of a[0..n) (values < 2^31 in total), returns the total.
-// Each lane scans a contiguous block serially, lane totals are combined with a warp scan.
-template <typename TT>
-__device__ __forceinline__ int warp_exclusive_scan_inplace(TT *a, int n, int lane, int *overflow_limit_total) {
-    const int per = (n + 31) >> 5;
-    const int b = lane * per;
-    const int e = min(b + per, n);
-    int s = 0;
-    for (int i = b; i < e; ++i) s += (int)a[i];
-    const int incl = warp_incl_scan(s, lane, 32);
-    const int total = __shfl_sync(FULL, incl, 31);
-    if (overflow_limit_total && total > *overflow_limit_total) return total;  // caller bails out
-    int run = incl - s;
-    for (int i = b; i < e; ++i) {
-        const int v = (int)a[i];
-        a[i] = (TT)run;
-        run += v;
-    }
-    return total;
-}
-
-struct Smem {
-    uint16_t *nbr;
-    void *off;
-    uint32_t *sn;
-    uint16_t *listA, *listB, *pos;
-    uint16_t *h16;     // = listA; listB and pos are h16 + oB, h16 + oP (index offsets in u16 units)
-    int oB, oP;
-    uint32_t *listC;   // last word of the array listA lives in: complexes grow downwards from it
-    uint64_t *spos;
-    uint16_t *cstart;
-    uint16_t *cfill;
-    uint4 *rng;
-};
-
-template <bool NBRG>
-__device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &l, uint16_t *nbr_scratch) {
-    Smem s;
-    s.nbr = NBRG ? nbr_scratch + (size_t)blockIdx.x * (size_t)l.cap : reinterpret_cast<uint16_t *>(base);
-    s.cfill = reinterpret_cast<uint16_t *>(base + l.o_cfill);
-    s.off = base + l.o_off;
-    s.sn = reinterpret_cast<uint32_t *>(base + l.o_sn);
-    s.listA = reinterpret_cast<uint16_t *>(base + l.o_listA);
-    s.listB = reinterpret_cast<uint16_t *>(base + l.o_listB);
-    s.pos = reinterpret_cast<uint16_t *>(base + l.o_pos);
-    s.h16 = s.listA;
-    s.oB = (l.o_listB - l.o_listA) / 2;
-    s.oP = (l.o_pos - l.o_listA) / 2;
-    s.listC = reinterpret_cast<uint32_t *>(base + l.o_listC);
-    s.spos = reinterpret_cast<uint64_t *>(base + l.o_spos);
-    s.cstart = reinterpret_cast<uint16_t *>(base + l.o_cstart);
-    s.rng = reinterpret_cast<uint4 *>(base + l.o_rng);
-    return s;
-}
-
 // ------------------------------------------------------------------------------------------------
 // K2: neighbour table of one trajectory with freshly sampled positions.
-//   positions: particle i (0..N-1) gets lattice coordinates Philox(i, STREAM_POSITIONS, rep, pidx),
-//              x = k * L * 2^-32 in [0, L)          (forward_simulator.jl:42-47: L*rand())
+//   positions: particle i (0..N-1) gets lattice coordinates k_d = top 21 bits of word d of
+//              Philox(i, STREAM_POSITIONS, rep, pidx), x_d = k_d L 2^-21 in [0, L)
+//              (forward_simulator.jl:42-47: L*rand())
 //   numbering: particles are renumbered by (cell id, i) with a stable counting sort
-//   table:     neighbours of particle i in (dz,dy,dx) lexicographic cell order, ascending sorted
-//              index inside a cell                   (forward_simulator.jl:52-61, 71-86)
-// Returns the number of directed entries, or -1 when it exceeds `cap`.
+//   table:     neighbours of particle i in (dz,dy,dx) lexicographic order of the cell offsets,
+//              ascending sorted index inside a cell  (forward_simulator.jl:52-61, 71-86)
+// Coordinates are kept pre-shifted (k << 11): the difference of two of them wraps at 2^32 exactly as the
+// lattice wraps at 2^21, so the min-image distance per axis is |int32(xj - xi)| >> 11 -- the
+// reference's min(|dx|, L-|dx|) (forward_simulator.jl:1-8) evaluated without rounding on the lattice;
+// the squared distance (< 2^42) is compared with r2lat = floor(reach^2 / (L 2^-21)^2) in 64-bit integers.
 // ------------------------------------------------------------------------------------------------
-template <int DIM, typename OffT>
-__device__ int build_table_resampled(const Smem &sm, int N, double L, double reach, int cap, uint32_t rep,
-                                     uint32_t pidx, uint32_t k0, uint32_t k1, int lane) {
-    OffT *off = reinterpret_cast<OffT *>(sm.off);
-    const int nc = cells_per_axis(N, DIM, L, reach);
-    int ncell = nc;
-#pragma unroll
-    for (int d = 1; d < DIM; ++d) ncell *= nc;
-    const unsigned long long r2lat = reach2_lattice(L, reach);
+constexpr int K2_MIN_CTAS = 4;
 
-    for (int c = lane; c <= ncell; c += 32) sm.cstart[c] = 0;
-    __syncwarp();
-    // pass 1: particles per cell (count of cell c kept at cstart[c+1])
-    for (int base = 0; base < N; base += 32) {
-        const int i = base + lane;
-        uint32_t cell = 0x10000u + (uint32_t)lane;
-        if (i < N) cell = cell_of<DIM>(gen_position<DIM>((uint32_t)i, rep, pidx, k0, k1), (uint32_t)nc);
-        const uint32_t mask = __match_any_sync(FULL, cell);
-        if (i < N && (__ffs(mask) - 1) == lane) sm.cstart[cell + 1] += (uint16_t)__popc(mask);
-        __syncwarp();
-    }
-    // exclusive scan: cstart[c] = first sorted index of cell c, cstart[ncell] = N
-    {
-        // counts sit at cstart[1..ncell]; scanning them in place (inclusive into the same slots)
-        const int per = (ncell + 31) >> 5;
-        const int b = lane * per, e = min(b + per, ncell);
-        int s = 0;
-        for (int c = b; c < e; ++c) s += sm.cstart[c + 1];
-        const int incl = warp_incl_scan(s, lane, 32);
-        int run = incl - s;
-        for (int c = b; c < e; ++c) {
-            run += sm.cstart[c + 1];
-            sm.cstart[c + 1] = (uint16_t)run;
-        }
-    }
-    __syncwarp();
-    for (int c = lane; c < ncell; c += 32) sm.cfill[c] = sm.cstart[c];
-    __syncwarp();
-    // pass 2: stable scatter into cell order
-    for (int base = 0; base < N; base += 32) {
-        const int i = base + lane;
-        uint32_t cell = 0x10000u + (uint32_t)lane;
-        uint64_t pk = 0;
-        if (i < N) {
-            pk = gen_position<DIM>((uint32_t)i, rep, pidx, k0, k1);
-            cell = cell_of<DIM>(pk, (uint32_t)nc);
-        }
-        const uint32_t mask = __match_any_sync(FULL, cell);
-        int slot = 0;
-        if (i < N) slot = sm.cfill[cell] + __popc(mask & lanemask_lt());
-        __syncwarp();
-        if (i < N) {
-            sm.spos[slot] = pk;
-            if ((__ffs(mask) - 1) == lane) sm.cfill[cell] += (uint16_t)__popc(mask);
-        }
-        __syncwarp();
-    }
-    // pass 3: the table, one particle per warp iteration.  The candidates of particle i are the
-    // particles of the 3^DIM cells around it in (dz,dy,dx) order; the three x-cells of a (dz,dy) row are
-    // contiguous in the sorted numbering except across the periodic wrap, so they form nr <= 2*3^(DIM-1)
-    // index ranges.  One lane per range computes (first index, length); a warp scan turns the lengths
-    // into positions in the flattened candidate list, the ranges are expanded into a 256-entry window
-    // (it lives in the idle rng block), and all 32 lanes then test consecutive candidates and append
-    // the hits in order with a ballot prefix: no second counting pass and no idle lanes.  Consecutive
-    // particles of the same cell reuse the expanded list.
-    uint16_t *cand = reinterpret_cast<uint16_t *>(sm.rng);
-    constexpr int WIN = 256;
-    const int nrow = nc >= 3 ? (DIM == 3 ? 9 : 3) : 1;
-    int running = 0;
-    if (lane == 0) off[0] = 0;
-    int prev_cell = -1, start = 0, len = 0, jb = 0, ctot = 0, mxl = 0, nr = 1;
-    bool cand_ok = false;
+struct K2Smem {
+    uint32_t *px, *py, *pz;   // [N] cell-sorted pre-shifted lattice coordinates
+    uint64_t *tmp;            // [N] packed coordinates in generation order (dead after the sort) ...
+    uint32_t *off;            // ... [N+1] degrees, then CSR offsets (same memory)
+    uint32_t *cs;             // [ncell+1] cell starts
+};
+
+__host__ __device__ inline int k2_align16(int x) { return (x + 15) & ~15; }
+__host__ __device__ inline int k2_o_tmp(int N) { return k2_align16(12 * N); }
+__host__ __device__ inline int k2_o_cs(int N) { return k2_o_tmp(N) + k2_align16(8 * N > 4 * (N + 1) ? 8 * N : 4 * (N + 1)); }
+__host__ __device__ inline int k2_bytes(int N) { return k2_o_cs(N) + k2_align16(4 * (1024 + 2)); }
+
+template <int DIM, bool WRITE>
+__device__ __forceinline__ int scan_range(int i, uint32_t xi, uint32_t yi, uint32_t zi, int j0, int j1,
+                                          const K2Smem &s, unsigned long long r2lat, uint16_t *row, int cnt) {
 #pragma unroll 1
-    for (int i = 0; i < N; ++i) {
-        const uint64_t ki = sm.spos[i];
-        const int cx = (int)((pos_axis(ki, 0) * (uint32_t)nc) >> POS_BITS);
-        const int cy = (int)((pos_axis(ki, 1) * (uint32_t)nc) >> POS_BITS);
-        const int cz = DIM == 3 ? (int)((pos_axis(ki, 2) * (uint32_t)nc) >> POS_BITS) : 0;
-        const int cell = (cz * nc + cy) * nc + cx;
-        if (cell != prev_cell) {
-            prev_cell = cell;
-            cand_ok = false;
-            const bool edge = nc >= 3 && (cx == 0 || cx == nc - 1);
-            nr = nc < 3 ? 1 : (edge ? 2 * nrow : nrow);
-            len = 0;
-            jb = 0;
-            if (lane < nr) {
-                int ca = 0, cb = 1;
-                if (nc >= 3) {
-                    const int r = edge ? lane >> 1 : lane;
-                    const int half = edge ? lane & 1 : 0;
-                    int yy = cy + (DIM == 3 ? r % 3 : r) - 1;
-                    yy = yy < 0 ? yy + nc : (yy >= nc ? yy - nc : yy);
-                    int zz = 0;
-                    if (DIM == 3) {
-                        zz = cz + r / 3 - 1;
-                        zz = zz < 0 ? zz + nc : (zz >= nc ? zz - nc : zz);
-                    }
-                    const int rb = (zz * nc + yy) * nc;
-                    if (cx == 0) {
-                        if (half == 0) { ca = rb + nc - 1; cb = rb + nc; } else { ca = rb; cb = rb + 2; }
-                    } else if (cx == nc - 1) {
-                        if (half == 0) { ca = rb + nc - 2; cb = rb + nc; } else { ca = rb; cb = rb + 1; }
-                    } else {
-                        ca = rb + cx - 1; cb = rb + cx + 2;
-                    }
-                }
-                jb = sm.cstart[ca];
-                len = (int)sm.cstart[cb] - jb;
+    for (int j = j0; j < j1; ++j) {
+        uint32_t d = s.px[j] - xi;
+        uint32_t q = ((int32_t)d < 0 ? 0u - d : d) >> 11;
+        unsigned long long acc = (unsigned long long)q * q;
+        d = s.py[j] - yi;
+        q = ((int32_t)d < 0 ? 0u - d : d) >> 11;
+        acc += (unsigned long long)q * q;
+        if (DIM == 3) {
+            d = s.pz[j] - zi;
+            q = ((int32_t)d < 0 ? 0u - d : d) >> 11;
+            acc += (unsigned long long)q * q;
+        }
+        if (acc <= r2lat && j != i) {
+            if (WRITE) row[cnt] = (uint16_t)j;
+            ++cnt;
+        }
+    }
+    return cnt;
+}
+
+// all within-reach neighbours of sorted particle i, in the order of the specification
+template <int DIM, bool WRITE>
+__device__ __forceinline__ int particle_row(int i, int N, int nc, const K2Smem &s, unsigned long long r2lat,
+                                            uint16_t *row) {
+    const uint32_t xi = s.px[i], yi = s.py[i], zi = DIM == 3 ? s.pz[i] : 0u;
+    if (nc < 3) return scan_range<DIM, WRITE>(i, xi, yi, zi, 0, N, s, r2lat, row, 0);
+    const int cx = (int)__umulhi(xi, (uint32_t)nc);     // (k << 11) * nc >> 32 == (k * nc) >> 21
+    const int cy = (int)__umulhi(yi, (uint32_t)nc);
+    const int cz = DIM == 3 ? (int)__umulhi(zi, (uint32_t)nc) : 0;
+    int cnt = 0;
+#pragma unroll 1
+    for (int r = 0; r < (DIM == 3 ? 9 : 3); ++r) {
+        int yy = cy + (DIM == 3 ? r % 3 : r) - 1;
+        yy = yy < 0 ? yy + nc : (yy >= nc ? yy - nc : yy);
+        int zz = 0;
+        if (DIM == 3) {
+            zz = cz + r / 3 - 1;
+            zz = zz < 0 ? zz + nc : (zz >= nc ? zz - nc : zz);
+        }
+        const int rb = (zz * nc + yy) * nc;
+        // the three x-cells of a row are contiguous in the sorted numbering except across the wrap
+        int a1, b1, a2 = 0, b2 = 0;
+        if (cx == 0) {
+            a1 = rb + nc - 1; b1 = rb + nc; a2 = rb; b2 = rb + 2;
+        } else if (cx == nc - 1) {
+            a1 = rb + nc - 2; b1 = rb + nc; a2 = rb; b2 = rb + 1;
+        } else {
+            a1 = rb + cx - 1; b1 = rb + cx + 2;
+        }
+        cnt = scan_range<DIM, WRITE>(i, xi, yi, zi, (int)s.cs[a1], (int)s.cs[b1], s, r2lat, row, cnt);
+        if (b2 > a2) cnt = scan_range<DIM, WRITE>(i, xi, yi, zi, (int)s.cs[a2], (int)s.cs[b2], s, r2lat, row, cnt);
+    }
+    return cnt;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(const TableArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ long long s_ticket;
+    __shared__ unsigned long long s_base;
+    __shared__ unsigned int s_maxdeg;
+    const int N = a.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    K2Smem s;
+    s.px = reinterpret_cast<uint32_t *>(smem_raw);
+    s.py = s.px + N;
+    s.pz = s.py + N;
+    s.tmp = reinterpret_cast<uint64_t *>(smem_raw + k2_o_tmp(N));
+    s.off = reinterpret_cast<uint32_t *>(s.tmp);
+    s.cs = reinterpret_cast<uint32_t *>(smem_raw + k2_o_cs(N));
+
+    for (;;) {
+        __syncthreads();                          // everyone is done with s_ticket / s_base of the previous ticket
+        if (tid == 0) {
+            s_ticket = (long long)atomicAdd(a.ctr + CTR_K2_TICKET, 1ULL);
+            s_maxdeg = 0u;
+        }
+        __syncthreads();
+        const long long q = s_ticket;
+        if (q >= a.ntickets) break;
+        const long long tk = a.ticket_list ? a.ticket_list[q] : a.tk0 + q;
+        const int slot = a.order[tk / a.nrep];
+        const uint32_t rep = (uint32_t)(a.rep0 + (int)(tk % a.nrep));
+        const double reach = a.pts[slot].reach;
+        const uint32_t pidx = a.pidx[slot];
+        const int nc = cells_per_axis(N, DIM, a.L, reach);
+        int ncell = nc;
+#pragma unroll
+        for (int d = 1; d < DIM; ++d) ncell *= nc;
+        const unsigned long long r2lat = reach2_lattice(a.L, reach);
+
+        // ---- positions (all threads) and particles per cell (count of cell c kept at cs[c+1])
+        for (int c = tid; c <= ncell; c += K2_THREADS) s.cs[c] = 0u;
+        __syncthreads();
+        for (int i = tid; i < N; i += K2_THREADS) {
+            const u32x4 r = philox4x32_10((uint32_t)i, STREAM_POSITIONS, rep, pidx, a.seed_lo, a.seed_hi);
+            const uint32_t kx = r.x >> (32 - POS_BITS), ky = r.y >> (32 - POS_BITS);
+            const uint32_t kz = DIM == 3 ? r.z >> (32 - POS_BITS) : 0u;
+            s.tmp[i] = (uint64_t)kx | ((uint64_t)ky << POS_BITS) | ((uint64_t)kz << (2 * POS_BITS));
+            const uint32_t cell = (((kz * (uint32_t)nc) >> POS_BITS) * (uint32_t)nc + ((ky * (uint32_t)nc) >> POS_BITS)) *
+                                      (uint32_t)nc + ((kx * (uint32_t)nc) >> POS_BITS);
+            atomicAdd(&s.cs[cell + 1], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // exclusive scan kept one slot up: cs[c+1] = first sorted index of cell c (the running fill
+            // pointer of the scatter below, which leaves cs[c] = first index of cell c, cs[ncell] = N)
+            const int per = (ncell + 31) >> 5;
+            const int b = lane * per, e = min(b + per, ncell);
+            int sum = 0;
+            for (int c = b; c < e; ++c) sum += (int)s.cs[c + 1];
+            int run = warp_incl_scan(sum, lane, 32) - sum;
+            for (int c = b; c < e; ++c) {
+                const int v = (int)s.cs[c + 1];
+                s.cs[c + 1] = (uint32_t)run;
+                run += v;
             }
-            const int incl = warp_incl_scan(len, lane, 32);
-            start = incl - len;
-            ctot = __shfl_sync(FULL, incl, 31);
-            mxl = __reduce_max_sync(FULL, len);
-        }
-#pragma unroll 1
-        for (int w0 = 0; w0 < ctot; w0 += WIN) {
-            const int wend = min(ctot - w0, WIN);
-            if (nr > 1 && !cand_ok) {
+            __syncwarp();
+            // stable scatter into cell order, 32 particles at a time in generation order
+            for (int base = 0; base < N; base += 32) {
+                const int i = base + lane;
+                uint32_t cell = 0x10000u + (uint32_t)lane;
+                uint32_t kx = 0, ky = 0, kz = 0;
+                if (i < N) {
+                    const uint64_t pk = s.tmp[i];
+                    kx = (uint32_t)pk & POS_MASK;
+                    ky = (uint32_t)(pk >> POS_BITS) & POS_MASK;
+                    kz = (uint32_t)(pk >> (2 * POS_BITS)) & POS_MASK;
+                    cell = (((kz * (uint32_t)nc) >> POS_BITS) * (uint32_t)nc + ((ky * (uint32_t)nc) >> POS_BITS)) *
+                               (uint32_t)nc + ((kx * (uint32_t)nc) >> POS_BITS);
+                }
+                const uint32_t mask = __match_any_sync(FULL, cell);
+                if (i < N) {
+                    const int dst = (int)s.cs[cell + 1] + __popc(mask & lanemask_lt());
+                    s.px[dst] = kx << 11;
+                    s.py[dst] = ky << 11;
+                    if (DIM == 3) s.pz[dst] = kz << 11;
+                }
                 __syncwarp();
-#pragma unroll 1
-                for (int tt = 0; tt < mxl; ++tt) {
-                    const int pq = start + tt - w0;
-                    if (tt < len && (unsigned)pq < (unsigned)WIN) cand[pq] = (uint16_t)(jb + tt);
-                }
+                if (i < N && (__ffs(mask) - 1) == lane) s.cs[cell + 1] += (uint32_t)__popc(mask);
                 __syncwarp();
-                cand_ok = ctot <= WIN;      // a single window stays valid for the next particles of the cell
-            }
-#pragma unroll 1
-            for (int c0 = 0; c0 < wend; c0 += 32) {
-                const int f = c0 + lane;
-                int j = 0;
-                bool hit = false;
-                if (f < wend) {
-                    j = nr > 1 ? (int)cand[f] : w0 + f;       // a single range [0, N): the candidate is its own index
-                    hit = j != i && within_reach<DIM>(ki, sm.spos[j], r2lat);
-                }
-                const uint32_t bal = __ballot_sync(FULL, hit);
-                const int nh = __popc(bal);
-                if (running + nh > cap) return -1;
-                if (hit) sm.nbr[running + __popc(bal & lanemask_lt())] = (uint16_t)j;
-                running += nh;
             }
         }
-        if (lane == 0) off[i + 1] = (OffT)running;
+        __syncthreads();
+        // ---- pass A: degrees (tmp is dead: off aliases it)
+        unsigned int mydeg = 0u;
+        for (int i = tid; i < N; i += K2_THREADS) {
+            const int c = particle_row<DIM, false>(i, N, nc, s, r2lat, nullptr);
+            s.off[i + 1] = (uint32_t)c;
+            mydeg = max(mydeg, (unsigned int)c);
+        }
+        mydeg = __reduce_max_sync(FULL, mydeg);
+        if (lane == 0) atomicMax(&s_maxdeg, mydeg);
+        __syncthreads();
+        if (warp == 0) {
+            // inclusive scan of the degrees in place: off[0] = 0, off[i+1] = entries of particles 0..i
+            const int per = (N + 31) >> 5;
+            const int b = lane * per, e = min(b + per, N);
+            unsigned int sum = 0;
+            for (int i = b; i < e; ++i) sum += s.off[i + 1];
+            unsigned int run = (unsigned int)warp_incl_scan((int)sum, lane, 32) - sum;
+            for (int i = b; i < e; ++i) {
+                run += s.off[i + 1];
+                s.off[i + 1] = run;
+            }
+            if (lane == 0) s.off[0] = 0u;
+            __syncwarp();
+            if (lane == 0) {
+                // exactly-sized record from the arena (bump allocation)
+                const unsigned long long total = s.off[N];
+                const unsigned long long bytes = (unsigned long long)(((size_t)(N + 1) * 4 + 15) & ~(size_t)15) +
+                                                 ((total * 2ULL + 15ULL) & ~15ULL);
+                const unsigned long long at = atomicAdd(a.ctr + CTR_CURSOR, bytes);
+                if (at + bytes <= a.arena_bytes) {
+                    s_base = at;
+                    a.desc[q] = (unsigned long long)(uintptr_t)(a.arena + at);
+                    atomicMax(a.ctr + CTR_MAX_ENTRIES, total);
+                    atomicMax(a.ctr + CTR_MAX_DEGREE, (unsigned long long)s_maxdeg);
+                } else {
+                    s_base = ~0ULL;
+                    a.desc[q] = 0ULL;
+                    const unsigned long long w = atomicAdd(a.ctr + CTR_NDEFER, 1ULL);
+                    a.defer_list[w] = tk;
+                }
+            }
+        }
+        __syncthreads();
+        const unsigned long long at = s_base;
+        if (at == ~0ULL) continue;
+        // ---- pass B: the record
+        uint32_t *goff = reinterpret_cast<uint32_t *>(a.arena + at);
+        uint16_t *gnbr = reinterpret_cast<uint16_t *>(a.arena + at + (((size_t)(N + 1) * 4 + 15) & ~(size_t)15));
+        for (int i = tid; i <= N; i += K2_THREADS) goff[i] = s.off[i];
+        for (int i = tid; i < N; i += K2_THREADS) particle_row<DIM, true>(i, N, nc, s, r2lat, gnbr + s.off[i]);
+        if (a.spos_out && q == 0) {
+            for (int i = tid; i < N; i += K2_THREADS)
+                a.spos_out[i] = (uint64_t)(s.px[i] >> 11) | ((uint64_t)(s.py[i] >> 11) << POS_BITS) |
+                                (DIM == 3 ? (uint64_t)(s.pz[i] >> 11) << (2 * POS_BITS) : 0ULL);
+        }
     }
-    __syncwarp();
-    return running;
 }
 
 // ------------------------------------------------------------------------------------------------
 // K1: the trajectory.  All scalars (time, counts, list lengths) are warp-uniform registers; the 32
-// lanes share the neighbour updates, list scans, bin writes and random-number generation.
+// lanes share the neighbour updates, list scans, save-slot writes and random-number generation.
+// State word of a particle: state | nA << 2 | nB << (2 + CB), CB = 7 (uint16_t) or 15 (uint32_t) bits
+// per neighbour count; state codes follow the reference (forward_simulator.jl:123).
 // ------------------------------------------------------------------------------------------------
+template <typename SnT> struct SnTraits;
+template <> struct SnTraits<uint16_t> { static constexpr int SH_A = 2, SH_B = 9; static constexpr uint32_t MASK = 0x7fu; };
+template <> struct SnTraits<uint32_t> { static constexpr int SH_A = 2, SH_B = 17; static constexpr uint32_t MASK = 0x7fffu; };
 
 // Neighbour updates are split into a load (row offset, degree, this lane's neighbour) and an apply
 // (read-modify-write of the neighbour's state word), so that the loads of both members of a pair
@@ -302,29 +293,29 @@ struct NbrRow {
 };
 
 template <typename OffT>
-__device__ __forceinline__ NbrRow load_row(const uint16_t *nbr_lane, const OffT *off, int m, int lane) {
+__device__ __forceinline__ NbrRow load_row(const uint16_t *__restrict__ nbr_lane, const OffT *off, int m, int lane) {
     NbrRow r;
     r.o0 = (int)off[m];
     r.dg = (int)off[m + 1] - r.o0;
-    r.j = lane < r.dg ? (int)nbr_lane[r.o0] : 0;     // nbr_lane = nbr + lane
+    r.j = lane < r.dg ? (int)nbr_lane[r.o0] : 0;     // nbr_lane = nbr + lane (global memory, L2-resident)
     return r;
 }
 
-template <bool PAIR>
-__device__ __forceinline__ void apply_row(const Smem &sm, const NbrRow &r, uint32_t delta, int other, uint32_t extra,
-                                          int lane) {
+template <bool PAIR, typename SnT>
+__device__ __forceinline__ void apply_row(SnT *sn, const uint16_t *__restrict__ nbr, const NbrRow &r, uint32_t delta,
+                                          int other, uint32_t extra, int lane) {
     if (lane < r.dg) {
         uint32_t d = delta;
         if (PAIR && r.j == other) d += extra;
-        sm.sn[r.j] += d;
+        sn[r.j] = (SnT)((uint32_t)sn[r.j] + d);
     }
     if (__builtin_expect(r.dg > 32, 0)) {
 #pragma unroll 1
         for (int q = lane + 32; q < r.dg; q += 32) {
-            const int j = sm.nbr[r.o0 + q];
+            const int j = nbr[r.o0 + q];
             uint32_t d = delta;
             if (PAIR && j == other) d += extra;
-            sm.sn[j] += d;
+            sn[j] = (SnT)((uint32_t)sn[j] + d);
         }
     }
 }
@@ -354,54 +345,53 @@ __device__ __forceinline__ int scan_small(int v, int lane, int nact) {
     return v;
 }
 
-template <int DIM, typename OffT, bool NBRG>
-__global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
+constexpr int K1_THREADS = 32 * K1_MAX_WPC;
+
+template <typename SnT, typename OffT>
+__global__ void __launch_bounds__(K1_THREADS, 5) spr_traj_kernel(const TrajArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x;
-    const Smem sm = carve<NBRG>(smem_raw, a.lay, a.nbr_scratch);
-    const OffT *off = reinterpret_cast<const OffT *>(sm.off);
-    const uint16_t *nbr_lane = sm.nbr + lane;
+    using ST = SnTraits<SnT>;
+    constexpr int SH_A = ST::SH_A, SH_B = ST::SH_B;
+    constexpr uint32_t CMASK = ST::MASK;
+    const int lane = threadIdx.x & 31;
+    unsigned char *slice = smem_raw + (size_t)(threadIdx.x >> 5) * (size_t)a.lay.slice;
+    OffT *off = reinterpret_cast<OffT *>(slice + a.lay.o_off);
+    SnT *sn = reinterpret_cast<SnT *>(slice + a.lay.o_sn);
+    uint16_t *ab = reinterpret_cast<uint16_t *>(slice + a.lay.o_ab);    // A from the front, B from the back
+    uint16_t *pos = reinterpret_cast<uint16_t *>(slice + a.lay.o_pos);
+    uint16_t *cl = reinterpret_cast<uint16_t *>(slice + a.lay.o_cl);
     const int N = a.N, T = a.T;
+    const int NB = N - 1;                                            // B-list element k lives at ab[NB - k]
     const double tstop = a.tstop, toff = a.toff;
     const double *__restrict__ tsave = a.tsave;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
     for (;;) {
-        long long ticket = 0;
-        if (lane == 0) ticket = (long long)atomicAdd(a.ticket_ctr, 1ULL);
-        ticket = __shfl_sync(FULL, ticket, 0);
-        if (ticket >= a.ntickets) break;
-        const long long tk = a.ticket_list ? a.ticket_list[ticket] : ticket;
+        long long q = 0;
+        if (lane == 0) q = (long long)atomicAdd(a.ctr + CTR_K1_TICKET, 1ULL);
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= a.ntickets) break;
+        const long long tk = a.ticket_list ? a.ticket_list[q] : a.tk0 + q;
         const int slot = a.order[tk / a.nrep];
         const int rep = a.rep0 + (int)(tk % a.nrep);
+        const unsigned long long rec = a.slot_rec ? a.slot_rec[slot] : a.desc[q];
+        if (rec == 0ULL) continue;                                   // deferred by K2 (arena full)
         const PointDev pt = a.pts[slot];
         const uint32_t pidx = a.pidx[slot];
 
-        // ---------------- neighbour table
-        int entries;
-        if (a.g_off) {
-            OffT *offw = reinterpret_cast<OffT *>(sm.off);
-            for (int i = lane; i <= N; i += 32) offw[i] = (OffT)a.g_off[i];
-            entries = (int)a.g_off[N];
-            for (int q = lane; q < entries; q += 32) sm.nbr[q] = a.g_nbr[q];
-        } else {
-            entries = build_table_resampled<DIM, OffT>(sm, N, a.L, pt.reach, a.lay.cap, (uint32_t)rep, pidx,
-                                                       a.seed_lo, a.seed_hi, lane);
-        }
+        // ---- neighbour table: offsets into shared memory, entries stay in global memory
+        const uint32_t *__restrict__ goff = reinterpret_cast<const uint32_t *>((uintptr_t)rec);
+        const uint16_t *__restrict__ nbr =
+            reinterpret_cast<const uint16_t *>((uintptr_t)rec + (((size_t)(N + 1) * 4 + 15) & ~(size_t)15));
+        const uint16_t *__restrict__ nbr_lane = nbr + lane;
+        for (int i = lane; i <= N; i += 32) off[i] = (OffT)goff[i];
         __syncwarp();
-        if (entries < 0) {  // table larger than this launch's capacity: hand the ticket back
-            if (lane == 0) {
-                const unsigned int w = atomicAdd(a.ovf_count, 1u);
-                if (w < a.ovf_cap) a.ovf_list[w] = tk;
-            }
-            continue;
-        }
-        // ---------------- initial state: everything A (forward_simulator.jl:148-149)
+        // ---- initial state: everything A (forward_simulator.jl:148-149)
         for (int i = lane; i < N; i += 32) {
             const uint32_t deg = (uint32_t)off[i + 1] - (uint32_t)off[i];
-            sm.sn[i] = ST_A | (deg << SH_NA);
-            sm.listA[i] = (uint16_t)i;
-            sm.pos[i] = (uint16_t)i;
+            sn[i] = (SnT)(ST_A | (deg << SH_A));
+            ab[i] = (uint16_t)i;
+            pos[i] = (uint16_t)i;
         }
         __syncwarp();
 
@@ -422,26 +412,25 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
         uint16_t *crow = a.curve + row * (size_t)T;
         uint16_t *crow2 = a.curve2 ? a.curve2 + row * (size_t)T : nullptr;
         const int obs = a.observable;
+        // randoms of 32 consecutive draws, one draw per lane: {E = -log U (double), w2, w3}
+        uint32_t rEl = 0, rEh = 0, rz = 0, rw = 0;
 
         for (;;) {
-            // ---- randoms of this draw: {E = -log U (double), w2, w3}, generated 32 draws at a time
             if ((ndraw & 31u) == 0u) {
                 const u32x4 r = philox4x32_10(ndraw + (uint32_t)lane, STREAM_EVENTS, (uint32_t)rep, pidx,
                                               a.seed_lo, a.seed_hi);
                 const uint64_t k53 = (((uint64_t)r.x << 21) | (uint64_t)(r.y >> 11)) + 1ULL;
                 const double En = neg_log_u53(k53);
-                uint4 v;
-                v.x = (uint32_t)__double2loint(En);
-                v.y = (uint32_t)__double2hiint(En);
-                v.z = r.z;
-                v.w = r.w;
-                __syncwarp();
-                sm.rng[lane] = v;
-                __syncwarp();
+                rEl = (uint32_t)__double2loint(En);
+                rEh = (uint32_t)__double2hiint(En);
+                rz = r.z;
+                rw = r.w;
             }
-            const uint4 rv = sm.rng[ndraw & 31u];
+            const int src = (int)(ndraw & 31u);
+            const double E = __hiloint2double((int)__shfl_sync(FULL, rEh, src), (int)__shfl_sync(FULL, rEl, src));
+            const uint32_t vz = __shfl_sync(FULL, rz, src);
+            const uint32_t vw = __shfl_sync(FULL, rw, src);
             ++ndraw;
-            const double E = __hiloint2double((int)rv.y, (int)rv.x);
 
             // ---- total propensity (exact integer counts x rates)
             const double cA = __dmul_rn(kon, (double)cntA);
@@ -494,38 +483,39 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
             t = tn;
 
             // ---- channel selection
-            const double x = __dmul_rn(__dmul_rn((double)rv.z, 0x1.0p-32), a0);
+            const double x = __dmul_rn(__dmul_rn((double)vz, 0x1.0p-32), a0);
             if (x < cB) {
                 // A --> B (forward_simulator.jl:204-224) when x < cA, else B --> A (:228-253): the same
-                // code with the two lists swapped
-                const bool ab = x < cA;
-                const int ofrom = ab ? 0 : sm.oB, oto = ab ? sm.oB : 0;
-                const int nfrom = ab ? cntA : cntB, nto = ab ? cntB : cntA;
-                const int k = (int)__umulhi(rv.w, (uint32_t)nfrom);
-                const int m = sm.h16[ofrom + k];
-                const int lastm = sm.h16[ofrom + nfrom - 1];
-                sm.h16[ofrom + k] = (uint16_t)lastm;
-                sm.h16[sm.oP + lastm] = (uint16_t)k;
-                sm.h16[oto + nto] = (uint16_t)m;
-                sm.h16[sm.oP + m] = (uint16_t)nto;
-                const int dAB = ab ? 1 : -1;
+                // code with the two lists swapped (A list: ab[k], B list: ab[NB - k])
+                const bool isab = x < cA;
+                const int nfrom = isab ? cntA : cntB, nto = isab ? cntB : cntA;
+                const int k = (int)__umulhi(vw, (uint32_t)nfrom);
+                const int fk = isab ? k : NB - k;                       // slot of element k of the source list
+                const int fl = isab ? nfrom - 1 : NB - (nfrom - 1);     // slot of its last element
+                const int tl = isab ? NB - nto : nto;                   // slot appended to in the destination list
+                const int m = ab[fk];
+                const int lastm = ab[fl];
+                ab[fk] = (uint16_t)lastm;
+                pos[lastm] = (uint16_t)k;
+                ab[tl] = (uint16_t)m;
+                pos[m] = (uint16_t)nto;
+                const int dAB = isab ? 1 : -1;
                 cntA -= dAB;
                 cntB += dAB;
-                const uint32_t v = sm.sn[m];
-                nAB += dAB * (sn_nA(v) - sn_nB(v));
-                sm.sn[m] = (v & ~3u) | (ab ? ST_B : ST_A);          // idempotent: every lane stores the same word
-                const NbrRow row = load_row<OffT>(nbr_lane, off, m, lane);
-                const uint32_t dlt = (1u << SH_NB) - (1u << SH_NA);
-                apply_row<false>(sm, row, ab ? dlt : 0u - dlt, 0, 0u, lane);
+                const uint32_t v = sn[m];
+                nAB += dAB * ((int)((v >> SH_A) & CMASK) - (int)((v >> SH_B) & CMASK));
+                sn[m] = (SnT)((v & ~3u) | (isab ? ST_B : ST_A));       // idempotent: every lane stores the same word
+                const NbrRow rowm = load_row<OffT>(nbr_lane, off, m, lane);
+                const uint32_t dlt = (1u << SH_B) - (1u << SH_A);
+                apply_row<false, SnT>(sn, nbr, rowm, isab ? dlt : 0u - dlt, 0, 0u, lane);
                 __syncwarp();
             } else if (x < cP) {
                 // A + B --> C (:256-289): pair number k of the nAB active pairs, enumerated along the
                 // shorter of the A and B lists (weights nB resp. nA), then along the neighbour list.
-                int k = (int)__umulhi(rv.w, (uint32_t)nAB);
+                int k = (int)__umulhi(vw, (uint32_t)nAB);
                 const bool sideA = cntA <= cntB;
-                const uint16_t *list = sideA ? sm.listA : sm.listB;
                 const int len = sideA ? cntA : cntB;
-                const int sh = sideA ? SH_NB : SH_NA;
+                const int sh = sideA ? SH_B : SH_A;
                 const uint32_t want = sideA ? ST_B : ST_A;
                 int xsel = 0, ix = 0;
                 for (int c0 = 0; c0 < len; c0 += 32) {
@@ -533,8 +523,8 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
                     const int nact = min(32, len - c0);
                     int xm = 0, w = 0;
                     if (idx < len) {
-                        xm = list[idx];
-                        w = (int)((sm.sn[xm] >> sh) & CNT_MASK);
+                        xm = ab[sideA ? idx : NB - idx];
+                        w = (int)(((uint32_t)sn[xm] >> sh) & CMASK);
                     }
                     const int incl = scan_small(w, lane, nact);
                     const int tot = nact > 1 ? __shfl_sync(FULL, incl, nact - 1) : __shfl_sync(FULL, w, 0);
@@ -553,12 +543,12 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
                 {
                     const int o0 = (int)off[xsel], o1 = (int)off[xsel + 1];
                     for (int q0 = o0; q0 < o1; q0 += 32) {
-                        const int q = q0 + lane;
+                        const int qq = q0 + lane;
                         int j = 0;
                         bool ok = false;
-                        if (q < o1) {
-                            j = sm.nbr[q];
-                            ok = sn_state(sm.sn[j]) == want;
+                        if (qq < o1) {
+                            j = nbr[qq];
+                            ok = ((uint32_t)sn[j] & 3u) == want;
                         }
                         uint32_t bal = __ballot_sync(FULL, ok);
                         const int c = __popc(bal);
@@ -572,60 +562,62 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
                 }
                 const int ma = sideA ? xsel : ysel;   // the A member
                 const int mb = sideA ? ysel : xsel;   // the B member
-                const int ia = sideA ? ix : (int)sm.pos[ma];
-                const int ib = sideA ? (int)sm.pos[mb] : ix;
-                // remove from the A and B lists, append to the complex list
+                const int ia = sideA ? ix : (int)pos[ma];
+                const int ib = sideA ? (int)pos[mb] : ix;
+                // remove from the A and B lists, append to the complex list (partner kept in pos)
                 {
-                    const int lastA = sm.listA[cntA - 1];
-                    sm.listA[ia] = (uint16_t)lastA;
-                    sm.pos[lastA] = (uint16_t)ia;
+                    const int lastA = ab[cntA - 1];
+                    ab[ia] = (uint16_t)lastA;
+                    pos[lastA] = (uint16_t)ia;
                     --cntA;
-                    const int lastB = sm.listB[cntB - 1];
-                    sm.listB[ib] = (uint16_t)lastB;
-                    sm.pos[lastB] = (uint16_t)ib;
+                    const int lastB = ab[NB - (cntB - 1)];
+                    ab[NB - ib] = (uint16_t)lastB;
+                    pos[lastB] = (uint16_t)ib;
                     --cntB;
-                    *(sm.listC - cntC) = (uint32_t)ma | ((uint32_t)mb << 16);
+                    cl[cntC] = (uint16_t)ma;
+                    pos[ma] = (uint16_t)mb;
+                    pos[mb] = (uint16_t)ma;
                     ++cntC;
                 }
-                const uint32_t va = sm.sn[ma], vb = sm.sn[mb];
+                const uint32_t va = sn[ma], vb = sn[mb];
                 const NbrRow rowa = load_row<OffT>(nbr_lane, off, ma, lane);
                 const NbrRow rowb = load_row<OffT>(nbr_lane, off, mb, lane);
-                nAB -= sn_nB(va) + sn_nA(vb) - 1;
+                nAB -= (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) - 1;
                 __syncwarp();   // every lane has read va, vb before the partner words change
                 // a's neighbours lose an A neighbour, and b (one of them) drops B(2) -> C(0);
                 // b's neighbours lose a B neighbour, and a drops A(1) -> C(0)
-                apply_row<true>(sm, rowa, 0u - (1u << SH_NA), mb, 0u - 2u, lane);
+                apply_row<true, SnT>(sn, nbr, rowa, 0u - (1u << SH_A), mb, 0u - 2u, lane);
                 __syncwarp();
-                apply_row<true>(sm, rowb, 0u - (1u << SH_NB), ma, 0u - 1u, lane);
+                apply_row<true, SnT>(sn, nbr, rowb, 0u - (1u << SH_B), ma, 0u - 1u, lane);
                 __syncwarp();
             } else {
                 // C --> A + B (:291-344): complex k; the freed end is chosen by a fair coin (:300-307)
-                const int k = (int)__umulhi(rv.w, (uint32_t)cntC);
-                const uint32_t pr = *(sm.listC - k);
-                *(sm.listC - k) = *(sm.listC - (cntC - 1));
+                const int k = (int)__umulhi(vw, (uint32_t)cntC);
+                int ma = cl[k];                      // the member that was A when the complex formed
+                int mb = pos[ma];                    // its partner
+                cl[k] = cl[cntC - 1];
                 --cntC;
-                int ma = (int)(pr & 0xffffu), mb = (int)(pr >> 16);
-                if (rv.w & 1u) {
+                if (vw & 1u) {
                     const int tmp = ma;
                     ma = mb;
                     mb = tmp;
                 }
-                sm.listA[cntA] = (uint16_t)ma;
-                sm.pos[ma] = (uint16_t)cntA;
+                ab[cntA] = (uint16_t)ma;
+                pos[ma] = (uint16_t)cntA;
                 ++cntA;
-                sm.listB[cntB] = (uint16_t)mb;
-                sm.pos[mb] = (uint16_t)cntB;
+                ab[NB - cntB] = (uint16_t)mb;
+                pos[mb] = (uint16_t)cntB;
                 ++cntB;
-                const uint32_t va = sm.sn[ma], vb = sm.sn[mb];
+                const uint32_t va = sn[ma], vb = sn[mb];
                 const NbrRow rowa = load_row<OffT>(nbr_lane, off, ma, lane);
                 const NbrRow rowb = load_row<OffT>(nbr_lane, off, mb, lane);
-                nAB += sn_nB(va) + sn_nA(vb) + 1;
+                nAB += (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) + 1;
                 __syncwarp();
                 // a's neighbours gain an A neighbour, and b becomes B: C(0) -> B(2);
                 // b's neighbours gain a B neighbour, and a becomes A: C(0) -> A(1)
-                apply_row<true>(sm, rowa, 1u << SH_NA, mb, 2u, lane);
+                apply_row<true, SnT>(sn, nbr, rowa, 1u << SH_A, mb, 2u, lane);
                 __syncwarp();
-                apply_row<true>(sm, rowb, 1u << SH_NB, ma, 1u, lane);
+                apply_row<true, SnT>(sn, nbr, rowb, 1u << SH_B, ma, 1u, lane);
                 __syncwarp();
             }
             if (last) break;
@@ -644,26 +636,6 @@ __global__ void __launch_bounds__(32) spr_traj_kernel(const TrajArgs a) {
     }
 }
 
-// one-trajectory table dump (test hook): same device functions as K1
-template <int DIM, typename OffT>
-__global__ void __launch_bounds__(32) spr_table_dump_kernel(const TrajArgs a, uint32_t rep, int slot,
-                                                            uint32_t *off_out, uint16_t *nbr_out,
-                                                            uint64_t *spos_out, long long *total_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x;
-    const Smem sm = carve<false>(smem_raw, a.lay, nullptr);
-    const PointDev pt = a.pts[slot];
-    const int entries = build_table_resampled<DIM, OffT>(sm, a.N, a.L, pt.reach, a.lay.cap, rep, a.pidx[slot],
-                                                         a.seed_lo, a.seed_hi, lane);
-    __syncwarp();
-    if (lane == 0) *total_out = entries;
-    if (entries < 0) return;
-    const OffT *off = reinterpret_cast<const OffT *>(sm.off);
-    for (int i = lane; i <= a.N; i += 32) off_out[i] = (uint32_t)off[i];
-    for (int q = lane; q < entries; q += 32) nbr_out[q] = sm.nbr[q];
-    for (int q = lane; q < a.N; q += 32) spos_out[q] = sm.spos[q];
-}
-
 // ------------------------------------------------------------------------------------------------
 // K2b: neighbour table for fixed FP64 positions, the reference's arithmetic (d += min(|dx|, L-|dx|)^2
 // with separate roundings, forward_simulator.jl:1-8), neighbours in ascending particle index.
@@ -679,13 +651,14 @@ __device__ __forceinline__ double ref_dist_sq(const double *p, const double *q, 
 }
 
 __global__ void fixed_graph_count_kernel(const double *locs, int N, int DIM, double L, double reach2,
-                                         uint32_t *deg) {
+                                         uint32_t *deg, unsigned int *maxdeg) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     uint32_t c = 0;
     for (int j = 0; j < N; ++j)
         if (j != i && ref_dist_sq(locs + (size_t)i * DIM, locs + (size_t)j * DIM, DIM, L) <= reach2) ++c;
     deg[i] = c;
+    if (maxdeg) atomicMax(maxdeg, c);
 }
 
 __global__ void fixed_graph_scan_kernel(uint32_t *deg_off, int N, unsigned long long *total) {
@@ -837,134 +810,119 @@ __global__ void scatter_idx_kernel(const double *__restrict__ rows, const long l
     }
 }
 
-template <int DIM, typename OffT, bool NBRG>
-cudaError_t set_smem_attr(int bytes) {
+inline int align16(int x) { return (x + 15) & ~15; }
+
+template <int DIM>
+cudaError_t set_table_attr(int bytes) {
     static int configured = -1;
     if (bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<DIM, OffT, NBRG>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaError_t e = cudaFuncSetAttribute(spr_table_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
-        if (!NBRG) {
-            e = cudaFuncSetAttribute(spr_table_dump_kernel<DIM, OffT>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            if (e != cudaSuccess) return e;
-        }
         configured = bytes;
     }
     return cudaSuccess;
 }
 
-inline int align16(int x) { return (x + 15) & ~15; }
+template <typename SnT, typename OffT>
+cudaError_t set_traj_attr(int bytes) {
+    static int configured = -1;
+    if (bytes > configured) {
+        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<SnT, OffT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        configured = bytes;
+    }
+    return cudaSuccess;
+}
+
+template <typename F>
+cudaError_t dispatch_traj(int wide_sn, int wide_off, F &&f) {
+    if (wide_sn) return wide_off ? f(uint32_t{}, uint32_t{}) : f(uint32_t{}, uint16_t{});
+    return wide_off ? f(uint16_t{}, uint32_t{}) : f(uint16_t{}, uint16_t{});
+}
 
 }  // namespace
 
-SmemLayout make_layout(int N, int DIM, int cap, bool nbr_global) {
-    (void)DIM;
-    SmemLayout l;
-    if (cap < 1024) cap = 1024;
-    cap = (cap + 63) & ~63;
-    l.cap = cap;
-    l.wide_off = cap > 65535 ? 1 : 0;
-    l.nbr_global = nbr_global ? 1 : 0;
-    int o = 0;
-    // cfill (u16 per cell, <= min(N,1024) cells, setup only) aliases nbr, or off when nbr is in global memory
-    l.o_cfill = 0;
-    if (!nbr_global) o += align16(cap * 2);
-    l.o_off = o;
-    if (nbr_global) l.o_cfill = o;
-    o += align16((N + 1) * (l.wide_off ? 4 : 2));
-    l.o_region = o;
-    // state view: the A list (u16, from the front) and the complex list (u32 pairs, from the back) share
-    // one array of 2N bytes: cntA + 2 cntC <= N always
-    int s = o;
-    l.o_sn = s;      s += align16(N * 4);
-    l.o_listA = s;
-    const int ac_words = (2 * N + 3) / 4;
-    l.o_listC = s + 4 * (ac_words - 1);          // address of the LAST word
-    s += align16(4 * ac_words);
-    l.o_listB = s;   s += align16(N * 2);
-    l.o_pos = s;     s += align16(N * 2);
-    // setup view: packed lattice positions (8 B per particle) and the cell starts
-    int u = o;
-    l.o_spos = u;    u += align16(N * 8);
-    l.o_cstart = u;  u += align16((1024 + 2) * 2);
-    o = s > u ? s : u;
-    l.o_rng = o;
-    o += 32 * 16;
-    l.total = o;
-    return l;
-}
+int table_smem_bytes(int N) { return k2_bytes(N); }
 
-int max_dynamic_smem(int device) {
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return 0;
-    return v;
-}
-
-// (DIM, offset width, table placement) -> template instantiation
-template <typename F>
-cudaError_t dispatch(int DIM, int wide, int nbrg, F &&f) {
-    using I3 = std::integral_constant<int, 3>;
-    using I2 = std::integral_constant<int, 2>;
-    using TT = std::true_type;
-    using FF = std::false_type;
-    if (DIM == 3) {
-        if (wide) return nbrg ? f(I3{}, uint32_t{}, TT{}) : f(I3{}, uint32_t{}, FF{});
-        return nbrg ? f(I3{}, uint16_t{}, TT{}) : f(I3{}, uint16_t{}, FF{});
-    }
-    if (wide) return nbrg ? f(I2{}, uint32_t{}, TT{}) : f(I2{}, uint32_t{}, FF{});
-    return nbrg ? f(I2{}, uint16_t{}, TT{}) : f(I2{}, uint16_t{}, FF{});
-}
-
-cudaError_t launch_traj(const TrajArgs &a, int DIM, int nblocks, cudaStream_t st) {
-    return dispatch(DIM, a.lay.wide_off, a.lay.nbr_global, [&](auto dim_c, auto off_t, auto g_c) -> cudaError_t {
-        constexpr int D_ = decltype(dim_c)::value;
-        using O_ = decltype(off_t);
-        constexpr bool G_ = decltype(g_c)::value;
-        cudaError_t e = set_smem_attr<D_, O_, G_>(a.lay.total);
-        if (e != cudaSuccess) return e;
-        spr_traj_kernel<D_, O_, G_><<<nblocks, 32, a.lay.total, st>>>(a);
-        return cudaGetLastError();
-    });
-}
-
-int traj_blocks_per_sm(const SmemLayout &lay, int DIM) {
+int table_ctas_per_sm(int N, int DIM) {
     int nb = 0;
-    cudaError_t e = dispatch(DIM, lay.wide_off, lay.nbr_global, [&](auto dim_c, auto off_t, auto g_c) -> cudaError_t {
-        constexpr int D_ = decltype(dim_c)::value;
-        using O_ = decltype(off_t);
-        constexpr bool G_ = decltype(g_c)::value;
-        cudaError_t e2 = set_smem_attr<D_, O_, G_>(lay.total);
-        if (e2 != cudaSuccess) return e2;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spr_traj_kernel<D_, O_, G_>, 32, lay.total);
-    });
-    return e == cudaSuccess ? nb : 0;
+    const int bytes = k2_bytes(N);
+    cudaError_t e;
+    if (DIM == 3) {
+        e = set_table_attr<3>(bytes);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spr_table_kernel<3>, K2_THREADS, bytes);
+    } else {
+        e = set_table_attr<2>(bytes);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spr_table_kernel<2>, K2_THREADS, bytes);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return nb;
 }
 
-cudaError_t launch_table_dump(const TrajArgs &a, int DIM, uint32_t replicate, int slot, uint32_t *d_off_out,
-                              uint16_t *d_nbr_out, uint64_t *d_spos_out, long long *d_total_out,
-                              cudaStream_t st) {
-    return dispatch(DIM, a.lay.wide_off, 0, [&](auto dim_c, auto off_t, auto) -> cudaError_t {
-        constexpr int D_ = decltype(dim_c)::value;
-        using O_ = decltype(off_t);
-        cudaError_t e = set_smem_attr<D_, O_, false>(a.lay.total);
+cudaError_t launch_table(const TableArgs &a, int DIM, int nblocks, cudaStream_t st) {
+    const int bytes = k2_bytes(a.N);
+    if (DIM == 3) {
+        cudaError_t e = set_table_attr<3>(bytes);
         if (e != cudaSuccess) return e;
-        spr_table_dump_kernel<D_, O_><<<1, 32, a.lay.total, st>>>(a, replicate, slot, d_off_out, d_nbr_out,
-                                                                 d_spos_out, d_total_out);
+        spr_table_kernel<3><<<nblocks, K2_THREADS, bytes, st>>>(a);
+    } else {
+        cudaError_t e = set_table_attr<2>(bytes);
+        if (e != cudaSuccess) return e;
+        spr_table_kernel<2><<<nblocks, K2_THREADS, bytes, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int smem_per_sm, TrajLayout *out) {
+    TrajLayout l{};
+    l.wide_sn = wide_sn ? 1 : 0;
+    l.wide_off = wide_off ? 1 : 0;
+    int o = 0;
+    l.o_off = o;  o += align16((N + 1) * (wide_off ? 4 : 2));
+    l.o_sn = o;   o += align16(N * (wide_sn ? 4 : 2));
+    l.o_ab = o;   o += align16(N * 2);
+    l.o_pos = o;  o += align16(N * 2);
+    l.o_cl = o;   o += align16((N / 2 + 1) * 2);
+    l.slice = o;
+    // warps per CTA: most resident trajectories per SM (every CTA also costs 1 KB of reserved shared memory)
+    int best = 0, best_w = 0, best_c = 0;
+    for (int w = 1; w <= K1_MAX_WPC; ++w) {
+        const long long bytes = (long long)w * l.slice;
+        if (bytes > smem_optin) break;
+        int c = (int)(smem_per_sm / (bytes + 1024));
+        if (c > 32) c = 32;
+        const int regcap = 25 / w;                     // 80 registers x 32 lanes: at most 25 warps per SM
+        if (c > regcap) c = regcap;
+        if (c * w > best) { best = c * w; best_w = w; best_c = c; }
+    }
+    l.wpc = best_w;
+    l.cta_per_sm = best_c;
+    *out = l;
+    return best > 0;
+}
+
+cudaError_t launch_traj(const TrajArgs &a, int nblocks, cudaStream_t st) {
+    return dispatch_traj(a.lay.wide_sn, a.lay.wide_off, [&](auto sn_t, auto off_t) -> cudaError_t {
+        using S_ = decltype(sn_t);
+        using O_ = decltype(off_t);
+        const int bytes = a.lay.slice * a.lay.wpc;
+        cudaError_t e = set_traj_attr<S_, O_>(bytes);
+        if (e != cudaSuccess) return e;
+        spr_traj_kernel<S_, O_><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
         return cudaGetLastError();
     });
 }
 
-cudaError_t launch_fixed_graph(const double *d_locs, int N, int DIM, double L, double reach, uint32_t *d_deg_off,
+cudaError_t launch_fixed_graph(const double *d_locs, int N, int DIM, double L, double reach, uint32_t *d_off,
                                uint16_t *d_nbr, long long nbr_cap, unsigned long long *d_total,
-                               cudaStream_t st) {
+                               unsigned int *d_maxdeg, cudaStream_t st) {
     const double reach2 = reach * reach;
     const int nb = (N + 127) / 128;
     if (d_nbr == nullptr) {
-        fixed_graph_count_kernel<<<nb, 128, 0, st>>>(d_locs, N, DIM, L, reach2, d_deg_off);
-        fixed_graph_scan_kernel<<<1, 1024, 0, st>>>(d_deg_off, N, d_total);
+        fixed_graph_count_kernel<<<nb, 128, 0, st>>>(d_locs, N, DIM, L, reach2, d_off, d_maxdeg);
+        fixed_graph_scan_kernel<<<1, 1024, 0, st>>>(d_off, N, d_total);
     } else {
-        fixed_graph_fill_kernel<<<nb, 128, 0, st>>>(d_locs, N, DIM, L, reach2, d_deg_off, d_nbr, nbr_cap);
+        fixed_graph_fill_kernel<<<nb, 128, 0, st>>>(d_locs, N, DIM, L, reach2, d_off, d_nbr, nbr_cap);
     }
     return cudaGetLastError();
 }

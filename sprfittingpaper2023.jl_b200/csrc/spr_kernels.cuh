@@ -5,75 +5,103 @@
 
 namespace spr {
 
-struct PointDev {          // one parameter point as the kernel sees it
+struct PointDev {          // one parameter point as the kernels see it
     double kon_eff, koff, konb, reach;
 };
 
-// Byte offsets of the per-trajectory shared-memory arrays (one warp = one CTA = one trajectory).
-// [nbr | off | region | rng]; `region` is time-shared: during neighbour-table construction it holds
-// the cell-sorted lattice positions and the cell starts, afterwards the particle/list state.
-struct SmemLayout {
-    int o_off;     // OffT[N+1]   CSR offsets
-    int o_region;
-    int o_sn;      // u32[N]      state | nA<<2 | nB<<17
-    int o_listA;   // u16[N]      particles in state A
-    int o_listB;   // u16[N]      particles in state B
-    int o_pos;     // u16[N]      index of a particle in listA/listB
-    int o_listC;   // u32         LAST word of the array shared with listA; complexes (a | b<<16) grow down
-    int o_spos;    // u64[N]      (setup) packed 21-bit lattice positions, cell-sorted
-    int o_cstart;  // u16[ncell+1](setup) first sorted index of every cell
-    int o_rng;     // 32 x 16 B   block of pre-generated event randoms
-    int total;     // bytes of dynamic shared memory
-    int cap;       // nbr capacity (directed entries, u16 each)
-    int wide_off;  // OffT = uint32_t when cap > 65535
-    int o_cfill;   // u16[ncell]  (setup) aliases nbr (table in shared memory) or off (table in global memory)
-    int nbr_global;// neighbour table lives in a per-CTA slice of TrajArgs::nbr_scratch (L2-resident)
-                   // instead of shared memory: more trajectories per SM for wide tables
+// ------------------------------------------------------------------------------------------------
+// Work items.  A *ticket* is one trajectory: tk = (position in `order`) * nrep + (replicate - rep0).
+// A launch processes local tickets 0..ntickets-1; local ticket q is tk = ticket_list ? ticket_list[q]
+// : tk0 + q.  Both kernels are persistent and pull local tickets from a global counter.
+//
+// Neighbour-table record of one trajectory, written by K2 into the HBM arena and read by K1:
+//     [ off u32[N+1] | pad to 16 B | nbr u16[off[N]] | pad to 16 B ]
+// `desc[q]` holds the device address of the record of local ticket q, or 0 when the arena was full
+// (the ticket is then listed in `defer_list` and neither kernel simulates it in this launch).
+// ------------------------------------------------------------------------------------------------
+
+// slots of the counter block (unsigned long long each)
+enum { CTR_K2_TICKET = 0, CTR_CURSOR = 1, CTR_MAX_ENTRIES = 2, CTR_MAX_DEGREE = 3, CTR_NDEFER = 4, CTR_K1_TICKET = 5,
+       CTR_COUNT = 8 };
+
+struct TableArgs {                      // K2: spr_table_kernel
+    int N;
+    double L;
+    const PointDev *pts;                // [nslots]
+    const uint32_t *pidx;               // [nslots] RNG parameter index
+    const int32_t *order;               // work order -> slot (expensive points first)
+    long long tk0, ntickets;
+    const long long *ticket_list;       // optional explicit tickets
+    int rep0, nrep;
+    uint32_t seed_lo, seed_hi;
+    unsigned long long *ctr;            // counter block (CTR_*)
+    unsigned char *arena;
+    unsigned long long arena_bytes;
+    unsigned long long *desc;           // [ntickets]
+    long long *defer_list;              // [ntickets]
+    uint64_t *spos_out;                 // test hook: packed sorted lattice positions of local ticket 0, or nullptr
 };
 
 enum { OBS_TOTAL_BOUND = 0, OBS_TOTAL_A = 1, OBS_RAW_BC = 2 };
 
-struct TrajArgs {
-    int N, T;
-    double L, tstop, toff;
-    const double *tsave;            // [T] device
-    const PointDev *pts;            // [nslots]
-    const uint32_t *pidx;           // [nslots] RNG parameter index
-    const int32_t *order;           // [norder] work order -> slot (expensive points first)
-    long long ntickets;             // norder * nrep (or length of ticket_list)
-    const long long *ticket_list;   // optional explicit tickets (re-run after capacity overflow)
-    int rep0, nrep, repstride;      // replicates rep0 .. rep0+nrep-1; curve row stride per slot
-    int rep_rowbase;                // curve row of replicate r is r - rep_rowbase
-    uint32_t seed_lo, seed_hi;
-    unsigned long long *ticket_ctr; // global work counter
-    uint16_t *curve;                // [nslots][repstride][T]
-    uint16_t *curve2;               // second plane (OBS_RAW_BC: C counts) or nullptr
-    unsigned long long *nevents;    // [nslots]
-    int observable;
-    long long *ovf_list;            // tickets whose neighbour table exceeded `cap`
-    unsigned int *ovf_count;
-    unsigned int ovf_cap;
-    uint16_t *nbr_scratch;          // [nblocks][lay.cap] when lay.nbr_global
-    const uint32_t *g_off;          // fixed-position mode: shared CSR (else nullptr)
-    const uint16_t *g_nbr;
-    SmemLayout lay;
+// Byte offsets inside one warp's shared-memory slice of K1 (one warp = one trajectory).
+struct TrajLayout {
+    int o_off;      // OffT[N+1]   CSR offsets of the neighbour table
+    int o_sn;       // SnT[N]      state | nA << 2 | nB << (2 + CB)
+    int o_ab;       // u16[N]      particles in state A from the front, in state B from the back
+    int o_pos;      // u16[N]      A/B: index in its list; C: index of the partner
+    int o_cl;       // u16[N/2+1]  one member (the former A) of every complex
+    int slice;      // bytes per warp
+    int wide_sn;    // SnT = uint32_t (15-bit neighbour counts) instead of uint16_t (7-bit)
+    int wide_off;   // OffT = uint32_t (more than 65535 directed entries)
+    int wpc;        // warps (trajectories) per CTA
+    int cta_per_sm;
 };
 
-SmemLayout make_layout(int N, int DIM, int cap, bool nbr_global = false);
-int max_dynamic_smem(int device);
-// launches the persistent trajectory kernel: `nblocks` single-warp CTAs
-cudaError_t launch_traj(const TrajArgs &a, int DIM, int nblocks, cudaStream_t st);
-int traj_blocks_per_sm(const SmemLayout &lay, int DIM);
+struct TrajArgs {                       // K1: spr_traj_kernel
+    int N, T;
+    double tstop, toff;
+    const double *tsave;                // [T] device
+    const PointDev *pts;
+    const uint32_t *pidx;
+    const int32_t *order;
+    long long tk0, ntickets;
+    const long long *ticket_list;
+    int rep0, nrep, repstride;          // curve row stride per slot
+    int rep_rowbase;                    // curve row of replicate r is r - rep_rowbase
+    uint32_t seed_lo, seed_hi;
+    unsigned long long *ctr;
+    const unsigned long long *desc;     // [ntickets] record addresses (resampled positions) ...
+    const unsigned long long *slot_rec; // ... or one record per slot (fixed positions), else nullptr
+    uint16_t *curve;                    // [nslots][repstride][T]
+    uint16_t *curve2;                   // second plane (OBS_RAW_BC: C counts) or nullptr
+    unsigned long long *nevents;        // [nslots]
+    int observable;
+    TrajLayout lay;
+};
 
-// fixed-position neighbour table (K2b): FP64, the reference's periodic_dist_sq
+inline size_t align16z(size_t x) { return (x + 15) & ~(size_t)15; }
+inline size_t record_bytes(int N, unsigned long long entries) {
+    return align16z(sizeof(uint32_t) * (size_t)(N + 1)) + align16z(sizeof(uint16_t) * (size_t)entries);
+}
+
+// K2
+int table_smem_bytes(int N);
+int table_ctas_per_sm(int N, int DIM);
+cudaError_t launch_table(const TableArgs &a, int DIM, int nblocks, cudaStream_t st);
+constexpr int K2_THREADS = 256;
+
+// K1: picks the warps-per-CTA that keeps the most trajectories resident per SM; false if one slice does not fit
+bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int smem_per_sm, TrajLayout *out);
+cudaError_t launch_traj(const TrajArgs &a, int nblocks, cudaStream_t st);
+constexpr int K1_MAX_WPC = 5;          // __launch_bounds__(160, 5): 80 registers, 25 warps per SM
+
+// fixed-position neighbour table (K2b): FP64, the reference's periodic_dist_sq.
+// d_nbr == nullptr: degrees -> exclusive offsets in d_off[0..N] and the total in *d_total;
+// else: fill d_nbr (capacity nbr_cap entries) using the offsets.
 cudaError_t launch_fixed_graph(const double *d_locs, int N, int DIM, double L, double reach,
-                               uint32_t *d_deg_off /* N+1 */, uint16_t *d_nbr, long long nbr_cap,
-                               unsigned long long *d_total, cudaStream_t st);
-
-// one-trajectory neighbour-table dump (test hook)
-cudaError_t launch_table_dump(const TrajArgs &a, int DIM, uint32_t replicate, int slot,
-                              uint32_t *d_off_out, uint16_t *d_nbr_out, uint64_t *d_spos_out,
-                              long long *d_total_out, cudaStream_t st);
+                               uint32_t *d_off /* N+1 */, uint16_t *d_nbr, long long nbr_cap,
+                               unsigned long long *d_total, unsigned int *d_maxdeg, cudaStream_t st);
 
 // K3: replicate reduction / sequential-stop scan
 cudaError_t launch_reduce_fixed(const uint16_t *curve, int nslots, int repstride, int nrep, int T,

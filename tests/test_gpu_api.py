@@ -208,10 +208,12 @@ def test_error_behaviour(engine):
     assert out["n_used"][0] == 2 and out["sum"][0][0] == 0 and out["sum"][0][1] > 0
 
 
-def test_capacity_overflow_is_rerun(engine, oracle_libs):
-    """a trajectory whose neighbour table exceeds the launch's shared-memory capacity is handed back
-    and re-run in a wider launch; results stay bit-identical.  SPRB200_CAP_SCALE (test hook) shrinks
-    the a-priori capacity so that overflows actually happen."""
+def test_arena_chunks_and_deferred_tables(engine, oracle_libs):
+    """the neighbour tables of a launch live in an HBM arena: a small arena (SPRB200_TABLE_BYTES) cuts
+    the trajectories into several table-build + simulate rounds, and a table that does not fit what is
+    left of the arena is deferred to the next round, never dropped (SPRB200_CAP_SCALE, a test hook,
+    makes the a-priori size estimate too small so that this actually happens).  Results stay
+    bit-identical."""
     import sprb200
     from sprb200 import _lib
     tsave = np.linspace(0.0, 100.0, 11)
@@ -219,17 +221,31 @@ def test_capacity_overflow_is_rerun(engine, oracle_libs):
     pts = [[0.05, 0.05, 1.0, 30.0], [0.5, 0.1, 0.3, 22.0], [0.05, 0.02, 0.2, 35.0]]
     run = sprb200.make_run(nsims=20, seed=8)
     ref = engine.simulate(sim, pts, run)
-    os.environ["SPRB200_CAP_SCALE"] = "0.85"      # below the mean table size for most replicates at reach 30, 35
+    base_launches = engine.stats()["kernel_launches"]
+    for env in ({"SPRB200_TABLE_BYTES": str(200 * 1024)},
+                {"SPRB200_TABLE_BYTES": str(200 * 1024), "SPRB200_CAP_SCALE": "0.5"}):
+        os.environ.update(env)
+        try:
+            eng2 = sprb200.Engine(0)
+            out = eng2.simulate(sim, pts, run)
+            launches = eng2.stats()["kernel_launches"]
+            eng2.close()
+        finally:
+            for k in env:
+                del os.environ[k]
+        assert launches > base_launches, env
+        for k in ("sum", "sumsq", "n_events", "n_used"):
+            assert np.array_equal(out[k], ref[k]), (k, env)
+    # an arena smaller than a single table is an error, not a hang
+    os.environ["SPRB200_TABLE_BYTES"] = str(70 * 1024)
     try:
-        eng2 = sprb200.Engine(0)
-        out = eng2.simulate(sim, pts, run)
-        launches = eng2.stats()["kernel_launches"]
-        eng2.close()
+        eng3 = sprb200.Engine(0)
+        with pytest.raises(sprb200.SprB200Error) as e:
+            eng3.simulate(sim, [[0.05, 0.05, 1.0, 120.0]], sprb200.make_run(nsims=2, seed=8))
+        assert e.value.code == _lib.ERR_TOO_LARGE
+        eng3.close()
     finally:
-        del os.environ["SPRB200_CAP_SCALE"]
-    assert launches > engine_launches_for(engine, sim, pts, run)
-    for k in ("sum", "sumsq", "n_events", "n_used"):
-        assert np.array_equal(out[k], ref[k]), k
+        del os.environ["SPRB200_TABLE_BYTES"]
 
 
 def engine_launches_for(engine, sim, pts, run):
