@@ -127,6 +127,10 @@ const char *sprb200_last_error(sprb200_handle h);
 int sprb200_last_stats(sprb200_handle h, uint64_t *trajectories, uint64_t *events,
                        uint64_t *kernel_launches, double *device_ms);
 
+/* Device milliseconds of the last call spent in the neighbour-table kernel (K2) and in the trajectory
+ * kernel (K1), summed over their launches (CUDA events on the handle's stream). */
+int sprb200_last_kernel_ms(sprb200_handle h, double *table_ms, double *traj_ms);
+
 /* ---- helpers --------------------------------------------------------------------------- */
 /* L = (N / agc)^(1/DIM), agc = 6.02214076e-7*antigenconcen if convert_units (parameters.jl:138-139) */
 double sprb200_domain_length(int32_t N, int32_t DIM, double antigenconcen, int32_t convert_units);

@@ -21,4 +21,4 @@ for b in range(10):
 print("sum of classes %.1f ms, events %.3e" % (tot_ms, tot_ev))
 eng.build_indices(grid, sim, run, np.arange(1, 10001))
 st = eng.stats()
-print("whole C2      %.1f ms, events %.3e  ev/s %.3e" % (st["device_ms"], st["events"], st["events"] / st["device_ms"] * 1e3))
+print("whole C2      %.1f ms (K2 %.1f, K1 %.1f), events %.3e  ev/s %.3e" % (st["device_ms"], st["table_ms"], st["traj_ms"], st["events"], st["events"] / st["device_ms"] * 1e3))

@@ -14,18 +14,20 @@ def run(name, pt, nsims, tstop=600.0, toff=150.0, T=601):
     out = eng.simulate(sim, [pt], r, want=("n_events",))
     st = eng.stats()
     ev = st["events"]; ms = st["device_ms"]
-    print("%-34s traj %6d ev/traj %9.1f  dev %8.2f ms  %8.2f us/traj  ev/s %.3e" %
-          (name, nsims, ev / nsims, ms, ms * 1e3 / nsims, ev / (ms * 1e-3)), flush=True)
+    print("%-34s traj %6d ev/traj %9.1f  dev %8.2f ms (K2 %7.2f K1 %8.2f)  %7.2f us/traj  ev/s %.3e  K1 ev/s %.3e" %
+          (name, nsims, ev / nsims, ms, st["table_ms"], st["traj_ms"], ms * 1e3 / nsims, ev / (ms * 1e-3),
+           ev / (st["traj_ms"] * 1e-3)), flush=True)
 only = sys.argv[1] if len(sys.argv) > 1 else ""
 if only == "ncusetup":
-    run("ncu: setup only reach 15.3", [0.0, 0.1, 1.0, 15.29], 2072)
+    reach = float(sys.argv[2]) if len(sys.argv) > 2 else 15.29
+    run("ncu: setup only reach %.1f" % reach, [0.0, 0.1, 1.0, reach], 5920)
     sys.exit(0)
 if only == "ncu":
-    run("ncu: pingpong reach35", [1.0, 0.1, 3.0, 35.0], 2368, tstop=120.0, toff=60.0, T=121)
+    run("ncu: pingpong reach35", [1.0, 0.1, 3.0, 35.0], 3700, tstop=60.0, toff=30.0, T=61)
     sys.exit(0)
 # setup only: no events (kon = 0)
 for reach in (2.0, 15.29, 24.0, 35.0):
-    run("setup only reach %.1f" % reach, [0.0, 0.1, 1.0, reach], 14800)
+    run("setup only reach %.1f" % reach, [0.0, 0.1, 1.0, reach], 148000)
 # flips only (konb = 0): A<->B
 run("flips only kon=1 koff=1 reach15", [1.0, 1.0, 0.0, 15.29], 14800, tstop=50.0, toff=50.0, T=51)
 run("flips only kon=1 koff=1 reach35", [1.0, 1.0, 0.0, 35.0], 5920, tstop=50.0, toff=50.0, T=51)

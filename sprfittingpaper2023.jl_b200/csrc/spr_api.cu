@@ -63,11 +63,22 @@ struct sprb200_ctx {
         rows, locs, goff, gnbr, misc, table, arena, desc, defer, tickets, slotrec;
     // stats of the last call
     uint64_t st_traj = 0, st_events = 0, st_launches = 0;
-    double st_ms = 0.0;
+    double st_ms = 0.0, st_table_ms = 0.0, st_traj_ms = 0.0;
+    std::vector<cudaEvent_t> evpool;          // timing events of the K2 / K1 launches of the last call
+    size_t evused = 0;
+    cudaEvent_t next_event() {
+        if (evused == evpool.size()) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            evpool.push_back(e);
+        }
+        return evpool[evused++];
+    }
     size_t curve_budget = (size_t)8 << 30;    // SPRB200_CURVE_BYTES: replicate curves resident per batch
     size_t table_budget = (size_t)16 << 30;   // SPRB200_TABLE_BYTES: neighbour-table arena (K2 -> K1)
     double est_scale = 1.0;   // SPRB200_CAP_SCALE (test hook): scales the a-priori table size used for chunking
     int max_warps = 0;        // SPRB200_MAX_WARPS (experiment hook): cap on resident trajectories per SM
+    int k1_variant = 5;       // SPRB200_K1_VARIANT (experiment hook): trajectory-kernel instantiation (4 or 5)
 };
 
 namespace {
@@ -229,7 +240,9 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
     cudaStream_t s0 = h->stream[0];
 
     h->st_traj = h->st_events = h->st_launches = 0;
-    h->st_ms = 0.0;
+    h->st_ms = h->st_table_ms = h->st_traj_ms = 0.0;
+    h->evused = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_k2, ev_k1;
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, h->tsave.ensure(sizeof(double) * T));
     CUDA_TRY(h, cudaMemcpyAsync(h->tsave.p, sim->tsave, sizeof(double) * T, cudaMemcpyHostToDevice, s0));
@@ -415,7 +428,10 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                     ta.defer_list = h->defer.as<long long>();
                     ta.spos_out = nullptr;
                     const long long nblk = std::min<long long>(n, (long long)k2_ctas * h->num_sms);
+                    cudaEvent_t ea = h->next_event(), eb = h->next_event();
+                    if (ea && eb) cudaEventRecord(ea, s0);
                     CUDA_TRY(h, launch_table(ta, DIM, (int)nblk, s0));
+                    if (ea && eb) { cudaEventRecord(eb, s0); ev_k2.emplace_back(ea, eb); }
                     h->st_launches += 1;
                     CUDA_TRY(h, cudaMemcpyAsync(ctr, h->counters.p, sizeof(ctr), cudaMemcpyDeviceToHost, s0));
                     CUDA_TRY(h, cudaStreamSynchronize(s0));
@@ -438,7 +454,7 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                 if (ndefer < n) {
                     TrajLayout lay;
                     const bool wide_sn = ctr[CTR_MAX_DEGREE] > 127ULL, wide_off = ctr[CTR_MAX_ENTRIES] > 65535ULL;
-                    if (!make_traj_layout(N, wide_sn, wide_off, h->smem_optin, h->smem_per_sm, &lay)) {
+                    if (!make_traj_layout(N, wide_sn, wide_off, h->smem_optin, h->smem_per_sm, &lay, h->k1_variant)) {
                         free_graphs();
                         return fail(h, SPRB200_ERR_TOO_LARGE,
                                     "per-trajectory state (N=" + std::to_string(N) + ", max degree " +
@@ -468,7 +484,10 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                     a.lay = lay;
                     const long long nblk = std::min<long long>((n + lay.wpc - 1) / lay.wpc,
                                                                (long long)lay.cta_per_sm * h->num_sms);
+                    cudaEvent_t ea = h->next_event(), eb = h->next_event();
+                    if (ea && eb) cudaEventRecord(ea, s0);
                     CUDA_TRY(h, launch_traj(a, (int)nblk, s0));
+                    if (ea && eb) { cudaEventRecord(eb, s0); ev_k1.emplace_back(ea, eb); }
                     h->st_launches += 1;
                     // the arena, descriptors and ticket list are reused by the next chunk: stream order keeps
                     // this launch ahead of the next K2
@@ -525,6 +544,9 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
     float ms = 0.f;
     CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end));
     h->st_ms = ms;
+    for (auto &pr : ev_k2) { float v = 0.f; if (cudaEventElapsedTime(&v, pr.first, pr.second) == cudaSuccess) h->st_table_ms += v; }
+    for (auto &pr : ev_k1) { float v = 0.f; if (cudaEventElapsedTime(&v, pr.first, pr.second) == cudaSuccess) h->st_traj_ms += v; }
+    cudaGetLastError();
     free_graphs();
     return SPRB200_OK;
 }
@@ -644,6 +666,7 @@ int sprb200_create(int device_ordinal, sprb200_handle *out) {
         if (v > 0) h->table_budget = (size_t)v;
     }
     if (const char *env = std::getenv("SPRB200_MAX_WARPS")) h->max_warps = std::atoi(env);
+    if (const char *env = std::getenv("SPRB200_K1_VARIANT")) h->k1_variant = std::atoi(env) == 4 ? 4 : 5;
     if (const char *env = std::getenv("SPRB200_CAP_SCALE")) {
         const double v = std::atof(env);
         if (v > 0.0 && v <= 1.0) h->est_scale = v;
@@ -665,6 +688,7 @@ void sprb200_destroy(sprb200_handle h) {
     for (int s = 0; s < NSTREAM; ++s) {
         if (h->stream[s]) cudaStreamDestroy(h->stream[s]);
     }
+    for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
     if (h->ev_begin) cudaEventDestroy(h->ev_begin);
     if (h->ev_end) cudaEventDestroy(h->ev_end);
     delete h;
@@ -679,6 +703,13 @@ int sprb200_last_stats(sprb200_handle h, uint64_t *trajectories, uint64_t *event
     if (events) *events = h->st_events;
     if (kernel_launches) *kernel_launches = h->st_launches;
     if (device_ms) *device_ms = h->st_ms;
+    return SPRB200_OK;
+}
+
+int sprb200_last_kernel_ms(sprb200_handle h, double *table_ms, double *traj_ms) {
+    if (!h) return SPRB200_ERR_BAD_ARG;
+    if (table_ms) *table_ms = h->st_table_ms;
+    if (traj_ms) *traj_ms = h->st_traj_ms;
     return SPRB200_OK;
 }
 

@@ -292,15 +292,54 @@ struct NbrRow {
     int o0, dg, j;   // first entry, degree, neighbour handled by this lane (valid if lane < dg)
 };
 
+// Experiment switches (scripts/build_variants.py builds one library per combination, scripts/run_variants.py
+// times them on the C2 build; results in profiles/README.md).  Defaults = the fastest measured combination:
+//   SPR_DEFER    apply the neighbour updates of an event after the next event's waiting time has been
+//                computed (hides the table-load latency, but the generic two-row update costs more than it saves)
+//   SPR_PREFETCH prefetch.global.L2 of the whole table at trajectory start (no gain: K2's records are still in L2)
+//   SPR_LDMODE   table loads: 0 generic, 1 ld.global, 2 ld.global.nc
+//   SPR_SCAN     shuffle scan with one early exit instead of five
+//   SPR_KBIT     k-th set bit of a ballot by a second ballot instead of a clear-lowest-bit loop
+#ifndef SPR_DEFER
+#define SPR_DEFER 0
+#endif
+#ifndef SPR_PREFETCH
+#define SPR_PREFETCH 0
+#endif
+#ifndef SPR_LDMODE
+#define SPR_LDMODE 2
+#endif
+#ifndef SPR_SCAN
+#define SPR_SCAN 1
+#endif
+#ifndef SPR_KBIT
+#define SPR_KBIT 1
+#endif
+
+// table entries are written by K2 (an earlier launch) and only read here
+__device__ __forceinline__ int ld_nbr(const uint16_t *__restrict__ nbr, uint32_t q) {
+#if SPR_LDMODE == 1
+    unsigned short v;
+    asm("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(nbr + q));
+    return (int)v;
+#elif SPR_LDMODE == 2
+    return (int)__ldg(nbr + q);
+#else
+    return (int)nbr[q];
+#endif
+}
+
 template <typename OffT>
-__device__ __forceinline__ NbrRow load_row(const uint16_t *__restrict__ nbr_lane, const OffT *off, int m, int lane) {
+__device__ __forceinline__ NbrRow load_row(const uint16_t *__restrict__ nbr, const OffT *off, int m, int lane) {
     NbrRow r;
     r.o0 = (int)off[m];
     r.dg = (int)off[m + 1] - r.o0;
-    r.j = lane < r.dg ? (int)nbr_lane[r.o0] : 0;     // nbr_lane = nbr + lane (global memory, L2-resident)
+    r.j = lane < r.dg ? ld_nbr(nbr, (uint32_t)(r.o0 + lane)) : 0;
     return r;
 }
 
+// sn[j] += delta for every neighbour j of the row; the neighbour `other` (the partner of a pair event,
+// -1 for none) also takes `extra`, its own state change: pair events need no separate state write.
 template <bool PAIR, typename SnT>
 __device__ __forceinline__ void apply_row(SnT *sn, const uint16_t *__restrict__ nbr, const NbrRow &r, uint32_t delta,
                                           int other, uint32_t extra, int lane) {
@@ -312,7 +351,7 @@ __device__ __forceinline__ void apply_row(SnT *sn, const uint16_t *__restrict__ 
     if (__builtin_expect(r.dg > 32, 0)) {
 #pragma unroll 1
         for (int q = lane + 32; q < r.dg; q += 32) {
-            const int j = nbr[r.o0 + q];
+            const int j = ld_nbr(nbr, (uint32_t)(r.o0 + q));
             uint32_t d = delta;
             if (PAIR && j == other) d += extra;
             sn[j] = (SnT)((uint32_t)sn[j] + d);
@@ -320,7 +359,8 @@ __device__ __forceinline__ void apply_row(SnT *sn, const uint16_t *__restrict__ 
     }
 }
 
-// inclusive scan over the first nact (<= 32) lanes, unrolled with warp-uniform early exit
+// inclusive scan over the first nact (<= 32) lanes; the upper levels are skipped for short lists
+#if !SPR_SCAN
 __device__ __forceinline__ int scan_small(int v, int lane, int nact) {
     if (nact > 1) {
         int o = __shfl_up_sync(FULL, v, 1);
@@ -344,11 +384,28 @@ __device__ __forceinline__ int scan_small(int v, int lane, int nact) {
     }
     return v;
 }
+#else
+__device__ __forceinline__ int scan_small(int v, int lane, int nact) {
+    int o = __shfl_up_sync(FULL, v, 1);
+    if (lane >= 1) v += o;
+    o = __shfl_up_sync(FULL, v, 2);
+    if (lane >= 2) v += o;
+    if (nact > 4) {
+        o = __shfl_up_sync(FULL, v, 4);
+        if (lane >= 4) v += o;
+        o = __shfl_up_sync(FULL, v, 8);
+        if (lane >= 8) v += o;
+        o = __shfl_up_sync(FULL, v, 16);
+        if (lane >= 16) v += o;
+    }
+    return v;
+}
+#endif
 
-constexpr int K1_THREADS = 32 * K1_MAX_WPC;
-
-template <typename SnT, typename OffT>
-__global__ void __launch_bounds__(K1_THREADS, 5) spr_traj_kernel(const TrajArgs a) {
+// WPC = 5: 5 warps per CTA, 5 CTAs per SM (25 trajectories, 72 registers);
+// WPC = 4: 4 warps per CTA, 6 CTAs per SM (24 trajectories, 80 registers)
+template <typename SnT, typename OffT, int WPC>
+__global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(const TrajArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using ST = SnTraits<SnT>;
     constexpr int SH_A = ST::SH_A, SH_B = ST::SH_B;
@@ -383,9 +440,15 @@ __global__ void __launch_bounds__(K1_THREADS, 5) spr_traj_kernel(const TrajArgs 
         const uint32_t *__restrict__ goff = reinterpret_cast<const uint32_t *>((uintptr_t)rec);
         const uint16_t *__restrict__ nbr =
             reinterpret_cast<const uint16_t *>((uintptr_t)rec + (((size_t)(N + 1) * 4 + 15) & ~(size_t)15));
-        const uint16_t *__restrict__ nbr_lane = nbr + lane;
-        for (int i = lane; i <= N; i += 32) off[i] = (OffT)goff[i];
+                for (int i = lane; i <= N; i += 32) off[i] = (OffT)goff[i];
         __syncwarp();
+#if SPR_PREFETCH
+        {   // the entries were written by an earlier launch: pull them from HBM into L2 before the first event
+            const uint32_t nbytes = 2u * (uint32_t)off[N];
+            for (uint32_t o = 128u * (uint32_t)lane; o < nbytes; o += 128u * 32u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char *>(nbr) + o));
+        }
+#endif
         // ---- initial state: everything A (forward_simulator.jl:148-149)
         for (int i = lane; i < N; i += 32) {
             const uint32_t deg = (uint32_t)off[i + 1] - (uint32_t)off[i];
@@ -414,6 +477,16 @@ __global__ void __launch_bounds__(K1_THREADS, 5) spr_traj_kernel(const TrajArgs 
         const int obs = a.observable;
         // randoms of 32 consecutive draws, one draw per lane: {E = -log U (double), w2, w3}
         uint32_t rEl = 0, rEh = 0, rz = 0, rw = 0;
+        // Neighbour updates of the previous event, applied only after the next event's waiting time and
+        // channel have been computed (those need the counts alone): the global-memory latency of the rows
+        // overlaps that arithmetic.  Row a takes da (+ 2 ds for the partner `oa`), row b db (+ ds for `ob`).
+#if SPR_DEFER
+        NbrRow pa, pb;
+        pa.o0 = pa.dg = pa.j = 0;
+        pb = pa;
+        uint32_t da = 0, db = 0, ds = 0;
+        int oa = -1, ob = -1;
+#endif
 
         for (;;) {
             if ((ndraw & 31u) == 0u) {
@@ -484,6 +557,17 @@ __global__ void __launch_bounds__(K1_THREADS, 5) spr_traj_kernel(const TrajArgs 
 
             // ---- channel selection
             const double x = __dmul_rn(__dmul_rn((double)vz, 0x1.0p-32), a0);
+#define SPR_APPLY_PENDING()                                   \
+    do {                                                      \
+        apply_row<true, SnT>(sn, nbr, pa, da, oa, ds + ds, lane);   \
+        __syncwarp();                                         \
+        apply_row<true, SnT>(sn, nbr, pb, db, ob, ds, lane);        \
+        __syncwarp();                                         \
+    } while (0)
+#if SPR_DEFER
+            // ---- the previous event's neighbour updates land now (their loads were issued an event ago)
+            SPR_APPLY_PENDING();
+#endif
             if (x < cB) {
                 // A --> B (forward_simulator.jl:204-224) when x < cA, else B --> A (:228-253): the same
                 // code with the two lists swapped (A list: ab[k], B list: ab[NB - k])
@@ -505,10 +589,17 @@ __global__ void __launch_bounds__(K1_THREADS, 5) spr_traj_kernel(const TrajArgs 
                 const uint32_t v = sn[m];
                 nAB += dAB * ((int)((v >> SH_A) & CMASK) - (int)((v >> SH_B) & CMASK));
                 sn[m] = (SnT)((v & ~3u) | (isab ? ST_B : ST_A));       // idempotent: every lane stores the same word
-                const NbrRow rowm = load_row<OffT>(nbr_lane, off, m, lane);
                 const uint32_t dlt = (1u << SH_B) - (1u << SH_A);
+#if SPR_DEFER
+                pa = load_row<OffT>(nbr, off, m, lane);
+                pb.dg = 0;
+                da = isab ? dlt : 0u - dlt;
+                oa = -1;
+#else
+                const NbrRow rowm = load_row<OffT>(nbr, off, m, lane);
                 apply_row<false, SnT>(sn, nbr, rowm, isab ? dlt : 0u - dlt, 0, 0u, lane);
                 __syncwarp();
+#endif
             } else if (x < cP) {
                 // A + B --> C (:256-289): pair number k of the nAB active pairs, enumerated along the
                 // shorter of the A and B lists (weights nB resp. nA), then along the neighbour list.
@@ -527,7 +618,11 @@ __global__ void __launch_bounds__(K1_THREADS, 5) spr_traj_kernel(const TrajArgs 
                         w = (int)(((uint32_t)sn[xm] >> sh) & CMASK);
                     }
                     const int incl = scan_small(w, lane, nact);
+#if SPR_SCAN
+                    const int tot = __shfl_sync(FULL, incl, nact - 1);
+#else
                     const int tot = nact > 1 ? __shfl_sync(FULL, incl, nact - 1) : __shfl_sync(FULL, w, 0);
+#endif
                     if (k < tot) {
                         const uint32_t hit = __ballot_sync(FULL, k < incl);
                         const int Lh = __ffs(hit) - 1;
@@ -547,14 +642,20 @@ __global__ void __launch_bounds__(K1_THREADS, 5) spr_traj_kernel(const TrajArgs 
                         int j = 0;
                         bool ok = false;
                         if (qq < o1) {
-                            j = nbr[qq];
+                            j = ld_nbr(nbr, (uint32_t)qq);
                             ok = ((uint32_t)sn[j] & 3u) == want;
                         }
-                        uint32_t bal = __ballot_sync(FULL, ok);
+                        const uint32_t bal = __ballot_sync(FULL, ok);
                         const int c = __popc(bal);
                         if (k < c) {
-                            for (int r = 0; r < k; ++r) bal &= bal - 1u;
-                            ysel = __shfl_sync(FULL, j, __ffs(bal) - 1);
+#if SPR_KBIT
+                            // the lane holding set bit number k of the ballot
+                            const uint32_t pick = __ballot_sync(FULL, ok && __popc(bal & lanemask_lt()) == k);
+#else
+                            uint32_t pick = bal;
+                            for (int r = 0; r < k; ++r) pick &= pick - 1u;
+#endif
+                            ysel = __shfl_sync(FULL, j, __ffs(pick) - 1);
                             break;
                         }
                         k -= c;
@@ -580,16 +681,27 @@ __global__ void __launch_bounds__(K1_THREADS, 5) spr_traj_kernel(const TrajArgs 
                     ++cntC;
                 }
                 const uint32_t va = sn[ma], vb = sn[mb];
-                const NbrRow rowa = load_row<OffT>(nbr_lane, off, ma, lane);
-                const NbrRow rowb = load_row<OffT>(nbr_lane, off, mb, lane);
-                nAB -= (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) - 1;
-                __syncwarp();   // every lane has read va, vb before the partner words change
                 // a's neighbours lose an A neighbour, and b (one of them) drops B(2) -> C(0);
                 // b's neighbours lose a B neighbour, and a drops A(1) -> C(0)
+#if SPR_DEFER
+                pa = load_row<OffT>(nbr, off, ma, lane);
+                pb = load_row<OffT>(nbr, off, mb, lane);
+                nAB -= (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) - 1;
+                da = 0u - (1u << SH_A);
+                db = 0u - (1u << SH_B);
+                ds = 0u - 1u;
+                oa = mb;
+                ob = ma;
+#else
+                const NbrRow rowa = load_row<OffT>(nbr, off, ma, lane);
+                const NbrRow rowb = load_row<OffT>(nbr, off, mb, lane);
+                nAB -= (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) - 1;
+                __syncwarp();   // every lane has read va, vb before the partner words change
                 apply_row<true, SnT>(sn, nbr, rowa, 0u - (1u << SH_A), mb, 0u - 2u, lane);
                 __syncwarp();
                 apply_row<true, SnT>(sn, nbr, rowb, 0u - (1u << SH_B), ma, 0u - 1u, lane);
                 __syncwarp();
+#endif
             } else {
                 // C --> A + B (:291-344): complex k; the freed end is chosen by a fair coin (:300-307)
                 const int k = (int)__umulhi(vw, (uint32_t)cntC);
@@ -609,16 +721,27 @@ __global__ void __launch_bounds__(K1_THREADS, 5) spr_traj_kernel(const TrajArgs 
                 pos[mb] = (uint16_t)cntB;
                 ++cntB;
                 const uint32_t va = sn[ma], vb = sn[mb];
-                const NbrRow rowa = load_row<OffT>(nbr_lane, off, ma, lane);
-                const NbrRow rowb = load_row<OffT>(nbr_lane, off, mb, lane);
-                nAB += (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) + 1;
-                __syncwarp();
                 // a's neighbours gain an A neighbour, and b becomes B: C(0) -> B(2);
                 // b's neighbours gain a B neighbour, and a becomes A: C(0) -> A(1)
+#if SPR_DEFER
+                pa = load_row<OffT>(nbr, off, ma, lane);
+                pb = load_row<OffT>(nbr, off, mb, lane);
+                nAB += (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) + 1;
+                da = 1u << SH_A;
+                db = 1u << SH_B;
+                ds = 1u;
+                oa = mb;
+                ob = ma;
+#else
+                const NbrRow rowa = load_row<OffT>(nbr, off, ma, lane);
+                const NbrRow rowb = load_row<OffT>(nbr, off, mb, lane);
+                nAB += (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) + 1;
+                __syncwarp();
                 apply_row<true, SnT>(sn, nbr, rowa, 1u << SH_A, mb, 2u, lane);
                 __syncwarp();
                 apply_row<true, SnT>(sn, nbr, rowb, 1u << SH_B, ma, 1u, lane);
                 __syncwarp();
+#endif
             }
             if (last) break;
         }
@@ -823,11 +946,11 @@ cudaError_t set_table_attr(int bytes) {
     return cudaSuccess;
 }
 
-template <typename SnT, typename OffT>
+template <typename SnT, typename OffT, int WPC>
 cudaError_t set_traj_attr(int bytes) {
     static int configured = -1;
     if (bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<SnT, OffT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<SnT, OffT, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
         configured = bytes;
     }
@@ -873,7 +996,7 @@ cudaError_t launch_table(const TableArgs &a, int DIM, int nblocks, cudaStream_t 
     return cudaGetLastError();
 }
 
-bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int smem_per_sm, TrajLayout *out) {
+bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int smem_per_sm, TrajLayout *out, int variant) {
     TrajLayout l{};
     l.wide_sn = wide_sn ? 1 : 0;
     l.wide_off = wide_off ? 1 : 0;
@@ -886,17 +1009,19 @@ bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int sm
     l.slice = o;
     // warps per CTA: most resident trajectories per SM (every CTA also costs 1 KB of reserved shared memory)
     int best = 0, best_w = 0, best_c = 0;
-    for (int w = 1; w <= K1_MAX_WPC; ++w) {
+    const int wmax = variant == 4 ? 4 : 5;
+    for (int w = 1; w <= wmax; ++w) {
         const long long bytes = (long long)w * l.slice;
         if (bytes > smem_optin) break;
         int c = (int)(smem_per_sm / (bytes + 1024));
         if (c > 32) c = 32;
-        const int regcap = 25 / w;                     // 80 registers x 32 lanes: at most 25 warps per SM
+        const int regcap = (variant == 4 ? 24 : 25) / w;   // registers: at most 24 (80 regs) or 25 (72 regs) warps per SM
         if (c > regcap) c = regcap;
         if (c * w > best) { best = c * w; best_w = w; best_c = c; }
     }
     l.wpc = best_w;
     l.cta_per_sm = best_c;
+    l.variant = wmax;
     *out = l;
     return best > 0;
 }
@@ -906,9 +1031,15 @@ cudaError_t launch_traj(const TrajArgs &a, int nblocks, cudaStream_t st) {
         using S_ = decltype(sn_t);
         using O_ = decltype(off_t);
         const int bytes = a.lay.slice * a.lay.wpc;
-        cudaError_t e = set_traj_attr<S_, O_>(bytes);
-        if (e != cudaSuccess) return e;
-        spr_traj_kernel<S_, O_><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+        if (a.lay.variant == 4) {
+            cudaError_t e = set_traj_attr<S_, O_, 4>(bytes);
+            if (e != cudaSuccess) return e;
+            spr_traj_kernel<S_, O_, 4><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+        } else {
+            cudaError_t e = set_traj_attr<S_, O_, 5>(bytes);
+            if (e != cudaSuccess) return e;
+            spr_traj_kernel<S_, O_, 5><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+        }
         return cudaGetLastError();
     });
 }

@@ -56,6 +56,7 @@ struct TrajLayout {
     int wide_off;   // OffT = uint32_t (more than 65535 directed entries)
     int wpc;        // warps (trajectories) per CTA
     int cta_per_sm;
+    int variant;    // kernel instantiation: 5 (up to 5 warps per CTA, 72 registers) or 4 (4 warps, 80 registers)
 };
 
 struct TrajArgs {                       // K1: spr_traj_kernel
@@ -92,9 +93,9 @@ cudaError_t launch_table(const TableArgs &a, int DIM, int nblocks, cudaStream_t 
 constexpr int K2_THREADS = 256;
 
 // K1: picks the warps-per-CTA that keeps the most trajectories resident per SM; false if one slice does not fit
-bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int smem_per_sm, TrajLayout *out);
+bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int smem_per_sm, TrajLayout *out,
+                      int variant = 5);
 cudaError_t launch_traj(const TrajArgs &a, int nblocks, cudaStream_t st);
-constexpr int K1_MAX_WPC = 5;          // __launch_bounds__(160, 5): 80 registers, 25 warps per SM
 
 // fixed-position neighbour table (K2b): FP64, the reference's periodic_dist_sq.
 // d_nbr == nullptr: degrees -> exclusive offsets in d_off[0..N] and the total in *d_total;

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "lib", "libsprb200.so")
+LIB_PATH = os.environ.get("SPRB200_LIB") or os.path.join(_PKG, "lib", "libsprb200.so")
 
 ABI_VERSION = 1
 OK = 0
@@ -16,6 +16,7 @@ OBS_TOTAL_BOUND, OBS_TOTAL_A = 0, 1
 
 EXPORTS = [
     "sprb200_abi_version", "sprb200_create", "sprb200_destroy", "sprb200_last_error", "sprb200_last_stats",
+    "sprb200_last_kernel_ms",
     "sprb200_domain_length", "sprb200_grid_value", "sprb200_grid_point", "sprb200_simulate",
     "sprb200_simulate_raw", "sprb200_neighbor_table", "sprb200_build_slice", "sprb200_build_table",
     "sprb200_merge_slice", "sprb200_build_slice_device", "sprb200_scatter_table_device",
@@ -79,6 +80,8 @@ def load():
     L.sprb200_last_error.argtypes = [vp]
     L.sprb200_last_stats.restype = C.c_int
     L.sprb200_last_stats.argtypes = [vp, P(u64), P(u64), P(u64), P(dbl)]
+    L.sprb200_last_kernel_ms.restype = C.c_int
+    L.sprb200_last_kernel_ms.argtypes = [vp, P(dbl), P(dbl)]
     L.sprb200_domain_length.restype = dbl
     L.sprb200_domain_length.argtypes = [i32, i32, dbl, i32]
     L.sprb200_grid_value.restype = dbl
@@ -178,7 +181,10 @@ class Engine:
     def stats(self):
         t, e, k, ms = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_double()
         self.lib.sprb200_last_stats(self.h, C.byref(t), C.byref(e), C.byref(k), C.byref(ms))
-        return dict(trajectories=t.value, events=e.value, kernel_launches=k.value, device_ms=ms.value)
+        tm, jm = C.c_double(), C.c_double()
+        self.lib.sprb200_last_kernel_ms(self.h, C.byref(tm), C.byref(jm))
+        return dict(trajectories=t.value, events=e.value, kernel_launches=k.value, device_ms=ms.value,
+                    table_ms=tm.value, traj_ms=jm.value)
 
     @staticmethod
     def _points(points):
