@@ -60,7 +60,7 @@ struct sprb200_ctx {
     std::string err;
     // arenas
     DevBuf tsave, pts, pidx, order, curve, curve2, sum, sumsq, nused, nevents, nscanned, nstar, active, counters,
-        rows, locs, goff, gnbr, misc, table, arena, desc, defer, tickets, slotrec;
+        rows, locs, goff, gnbr, misc, table, arena, desc, defer, tickets, slotrec, stage;
     // stats of the last call
     uint64_t st_traj = 0, st_events = 0, st_launches = 0;
     double st_ms = 0.0, st_table_ms = 0.0, st_traj_ms = 0.0;
@@ -78,6 +78,7 @@ struct sprb200_ctx {
     size_t table_budget = (size_t)16 << 30;   // SPRB200_TABLE_BYTES: neighbour-table arena (K2 -> K1)
     double est_scale = 1.0;   // SPRB200_CAP_SCALE (test hook): scales the a-priori table size used for chunking
     int max_warps = 0;        // SPRB200_MAX_WARPS (experiment hook): cap on resident trajectories per SM
+    int stage_cap_override = 0;   // SPRB200_STAGE_CAP (test hook): staging stride of K2's distance pass
     int k1_variant = 5;       // SPRB200_K1_VARIANT (experiment hook): trajectory-kernel instantiation (4 or 5)
 };
 
@@ -258,6 +259,15 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
         k2_ctas = table_ctas_per_sm(N, DIM);
         if (k2_ctas < 1) return fail(h, SPRB200_ERR_TOO_LARGE, "neighbour-table kernel does not fit on an SM");
     }
+    // staging rows of K2's distance pass: one slice per resident CTA, stride set by the widest reach of the call
+    int stage_cap = 8;
+    if (!fixedpos) {
+        double maxreach = 0.0;
+        for (int64_t k = 0; k < npts; ++k) maxreach = std::max(maxreach, pts[k].reach);
+        stage_cap = table_stage_cap(N, DIM, sim->L, maxreach);
+        if (h->stage_cap_override > 0) stage_cap = std::min(stage_cap, std::max(1, h->stage_cap_override));
+        CUDA_TRY(h, h->stage.ensure(sizeof(uint16_t) * (size_t)k2_ctas * h->num_sms * (size_t)N * (size_t)stage_cap));
+    }
     {   // the narrowest trajectory layout must fit one warp's slice
         TrajLayout probe;
         if (!make_traj_layout(N, false, false, h->smem_optin, h->smem_per_sm, &probe))
@@ -427,6 +437,8 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                     ta.desc = h->desc.as<unsigned long long>();
                     ta.defer_list = h->defer.as<long long>();
                     ta.spos_out = nullptr;
+                    ta.stage = h->stage.as<uint16_t>();
+                    ta.stage_cap = stage_cap;
                     const long long nblk = std::min<long long>(n, (long long)k2_ctas * h->num_sms);
                     cudaEvent_t ea = h->next_event(), eb = h->next_event();
                     if (ea && eb) cudaEventRecord(ea, s0);
@@ -666,6 +678,7 @@ int sprb200_create(int device_ordinal, sprb200_handle *out) {
         if (v > 0) h->table_budget = (size_t)v;
     }
     if (const char *env = std::getenv("SPRB200_MAX_WARPS")) h->max_warps = std::atoi(env);
+    if (const char *env = std::getenv("SPRB200_STAGE_CAP")) h->stage_cap_override = std::atoi(env);
     if (const char *env = std::getenv("SPRB200_K1_VARIANT")) h->k1_variant = std::atoi(env) == 4 ? 4 : 5;
     if (const char *env = std::getenv("SPRB200_CAP_SCALE")) {
         const double v = std::atof(env);
@@ -683,7 +696,7 @@ void sprb200_destroy(sprb200_handle h) {
     }
     DevBuf *bufs[] = {&h->tsave, &h->pts, &h->pidx, &h->order, &h->curve, &h->curve2, &h->sum, &h->sumsq, &h->nused,
                       &h->nevents, &h->nscanned, &h->nstar, &h->active, &h->counters, &h->rows, &h->locs,
-                      &h->goff, &h->gnbr, &h->misc, &h->table, &h->arena, &h->desc, &h->defer, &h->tickets, &h->slotrec};
+                      &h->goff, &h->gnbr, &h->misc, &h->table, &h->arena, &h->desc, &h->defer, &h->tickets, &h->slotrec, &h->stage};
     for (DevBuf *b : bufs) b->release();
     for (int s = 0; s < NSTREAM; ++s) {
         if (h->stream[s]) cudaStreamDestroy(h->stream[s]);
@@ -858,6 +871,9 @@ int64_t sprb200_neighbor_table(sprb200_handle h, const SprSim *sim, double reach
         ta.arena = h->arena.as<unsigned char>(); ta.arena_bytes = h->arena.cap;
         ta.desc = h->desc.as<unsigned long long>(); ta.defer_list = h->defer.as<long long>();
         ta.spos_out = h->locs.as<uint64_t>();
+        ta.stage_cap = table_stage_cap(N, DIM, sim->L, reach);
+        CUDA_TRY(h, h->stage.ensure(sizeof(uint16_t) * (size_t)N * (size_t)ta.stage_cap));
+        ta.stage = h->stage.as<uint16_t>();
         CUDA_TRY(h, launch_table(ta, DIM, 1, s0));
         unsigned long long ctr[CTR_COUNT] = {};
         CUDA_TRY(h, cudaMemcpyAsync(ctr, h->counters.p, sizeof(ctr), cudaMemcpyDeviceToHost, s0));

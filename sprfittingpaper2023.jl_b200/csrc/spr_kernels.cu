@@ -47,46 +47,72 @@ __host__ __device__ inline unsigned long long reach2_lattice(double L, double re
 //   positions: particle i (0..N-1) gets lattice coordinates k_d = top 21 bits of word d of
 //              Philox(i, STREAM_POSITIONS, rep, pidx), x_d = k_d L 2^-21 in [0, L)
 //              (forward_simulator.jl:42-47: L*rand())
-//   numbering: particles are renumbered by (cell id, i) with a stable counting sort
+//   numbering: particles are renumbered by (cell id, i) -- a stable counting sort
 //   table:     neighbours of particle i in (dz,dy,dx) lexicographic order of the cell offsets,
 //              ascending sorted index inside a cell  (forward_simulator.jl:52-61, 71-86)
 // Coordinates are kept pre-shifted (k << 11): the difference of two of them wraps at 2^32 exactly as the
-// lattice wraps at 2^21, so the min-image distance per axis is |int32(xj - xi)| >> 11 -- the
-// reference's min(|dx|, L-|dx|) (forward_simulator.jl:1-8) evaluated without rounding on the lattice;
-// the squared distance (< 2^42) is compared with r2lat = floor(reach^2 / (L 2^-21)^2) in 64-bit integers.
+// lattice wraps at 2^21, so the min-image distance per axis is |int32(xj - xi)| = 2^11 min(|dk|, 2^21-|dk|)
+// -- the reference's min(|dx|, L-|dx|) (forward_simulator.jl:1-8) evaluated without rounding on the
+// lattice; the sum of squares (< 3 2^62) is compared with 2^22 floor(reach^2 / (L 2^-21)^2) in 64-bit integers.
+//
+// One 256-thread CTA per trajectory, one thread per particle:
+//   1. positions + arrival rank in the cell (shared-memory atomics), 2. cell starts (warp scan),
+//   3. stable placement (rank among the cell's particles by original index), 4. ONE distance pass that
+//   stages each particle's hits in a fixed-stride row of a per-CTA global scratch (L2-resident),
+//   5. degree scan + exactly-sized record from the arena, 6. compaction of the staged rows into the
+//   record.  A particle with more neighbours than the staging stride falls back to a second distance pass.
 // ------------------------------------------------------------------------------------------------
 constexpr int K2_MIN_CTAS = 4;
 
 struct K2Smem {
-    uint32_t *px, *py, *pz;   // [N] cell-sorted pre-shifted lattice coordinates
+    uint4 *p;                 // [N] cell-sorted pre-shifted lattice coordinates (x, y, z, original index)
     uint64_t *tmp;            // [N] packed coordinates in generation order (dead after the sort) ...
     uint32_t *off;            // ... [N+1] degrees, then CSR offsets (same memory)
-    uint32_t *cs;             // [ncell+1] cell starts
+    uint32_t *cs;             // [ncell+2]: cs[c+1] = first sorted index of cell c, cs[ncell+1] = N
+    uint16_t *seg;            // [N] original indices grouped by cell in arrival order
+    uint16_t *rk;             // [N] arrival rank of particle i in its cell
 };
 
 __host__ __device__ inline int k2_align16(int x) { return (x + 15) & ~15; }
-__host__ __device__ inline int k2_o_tmp(int N) { return k2_align16(12 * N); }
+__host__ __device__ inline int k2_o_tmp(int N) { return 16 * N; }
 __host__ __device__ inline int k2_o_cs(int N) { return k2_o_tmp(N) + k2_align16(8 * N > 4 * (N + 1) ? 8 * N : 4 * (N + 1)); }
-__host__ __device__ inline int k2_bytes(int N) { return k2_o_cs(N) + k2_align16(4 * (1024 + 2)); }
+__host__ __device__ inline int k2_o_seg(int N) { (void)N; return k2_o_cs(N) + k2_align16(4 * (1024 + 3)); }
+__host__ __device__ inline int k2_o_rk(int N) { return k2_o_seg(N) + k2_align16(2 * N); }
+__host__ __device__ inline int k2_bytes(int N) { return k2_o_rk(N) + k2_align16(2 * N); }
 
-template <int DIM, bool WRITE>
+// staging stride (entries per particle) for mean degree dbar: mean + 6 sigma, multiple of 8
+__host__ __device__ inline int k2_stage_cap(int N, int DIM, double L, double reach) {
+    const double PI = 3.14159265358979323846;
+    double frac = DIM == 3 ? (4.0 / 3.0) * PI * reach * reach * reach / (L * L * L) : PI * reach * reach / (L * L);
+    if (frac > 1.0) frac = 1.0;
+    const double dbar = (double)(N - 1) * frac;
+    double c = dbar + 6.0 * sqrt(dbar) + 8.0;
+    if (c > (double)(N - 1)) c = (double)(N - 1);
+    int cap = ((int)c + 7) & ~7;
+    return cap < 8 ? 8 : cap;
+}
+
+// MODE 0: count + stage (hits beyond `cap` are only counted); MODE 1: write every hit to `row`
+template <int DIM, int MODE>
 __device__ __forceinline__ int scan_range(int i, uint32_t xi, uint32_t yi, uint32_t zi, int j0, int j1,
-                                          const K2Smem &s, unsigned long long r2lat, uint16_t *row, int cnt) {
+                                          const uint4 *__restrict__ p, unsigned long long r2s, uint16_t *row, int cap,
+                                          int cnt) {
 #pragma unroll 1
     for (int j = j0; j < j1; ++j) {
-        uint32_t d = s.px[j] - xi;
-        uint32_t q = ((int32_t)d < 0 ? 0u - d : d) >> 11;
-        unsigned long long acc = (unsigned long long)q * q;
-        d = s.py[j] - yi;
-        q = ((int32_t)d < 0 ? 0u - d : d) >> 11;
-        acc += (unsigned long long)q * q;
+        const uint4 c = p[j];
+        uint32_t d = c.x - xi;
+        uint32_t m = (int32_t)d < 0 ? 0u - d : d;
+        unsigned long long acc = (unsigned long long)m * m;
+        d = c.y - yi;
+        m = (int32_t)d < 0 ? 0u - d : d;
+        acc += (unsigned long long)m * m;
         if (DIM == 3) {
-            d = s.pz[j] - zi;
-            q = ((int32_t)d < 0 ? 0u - d : d) >> 11;
-            acc += (unsigned long long)q * q;
+            d = c.z - zi;
+            m = (int32_t)d < 0 ? 0u - d : d;
+            acc += (unsigned long long)m * m;
         }
-        if (acc <= r2lat && j != i) {
-            if (WRITE) row[cnt] = (uint16_t)j;
+        if (acc <= r2s && j != i) {
+            if (MODE == 1 || cnt < cap) row[cnt] = (uint16_t)j;
             ++cnt;
         }
     }
@@ -94,38 +120,48 @@ __device__ __forceinline__ int scan_range(int i, uint32_t xi, uint32_t yi, uint3
 }
 
 // all within-reach neighbours of sorted particle i, in the order of the specification
-template <int DIM, bool WRITE>
-__device__ __forceinline__ int particle_row(int i, int N, int nc, const K2Smem &s, unsigned long long r2lat,
-                                            uint16_t *row) {
-    const uint32_t xi = s.px[i], yi = s.py[i], zi = DIM == 3 ? s.pz[i] : 0u;
-    if (nc < 3) return scan_range<DIM, WRITE>(i, xi, yi, zi, 0, N, s, r2lat, row, 0);
+template <int DIM, int MODE>
+__device__ __forceinline__ int particle_row(int i, int N, int nc, const K2Smem &s, unsigned long long r2s,
+                                            uint16_t *row, int cap) {
+    const uint4 me = s.p[i];
+    const uint32_t xi = me.x, yi = me.y, zi = DIM == 3 ? me.z : 0u;
+    if (nc < 3) return scan_range<DIM, MODE>(i, xi, yi, zi, 0, N, s.p, r2s, row, cap, 0);
+    const uint32_t *cs1 = s.cs + 1;                     // cs1[c] = first sorted index of cell c
     const int cx = (int)__umulhi(xi, (uint32_t)nc);     // (k << 11) * nc >> 32 == (k * nc) >> 21
     const int cy = (int)__umulhi(yi, (uint32_t)nc);
     const int cz = DIM == 3 ? (int)__umulhi(zi, (uint32_t)nc) : 0;
+    // the three x-cells of a (dz,dy) row are contiguous in the sorted numbering except across the wrap
+    int ax1, bx1, ax2 = 0, bx2 = 0;
+    if (cx == 0) {
+        ax1 = nc - 1; bx1 = nc; ax2 = 0; bx2 = 2;
+    } else if (cx == nc - 1) {
+        ax1 = nc - 2; bx1 = nc; ax2 = 0; bx2 = 1;
+    } else {
+        ax1 = cx - 1; bx1 = cx + 2;
+    }
     int cnt = 0;
 #pragma unroll 1
-    for (int r = 0; r < (DIM == 3 ? 9 : 3); ++r) {
-        int yy = cy + (DIM == 3 ? r % 3 : r) - 1;
-        yy = yy < 0 ? yy + nc : (yy >= nc ? yy - nc : yy);
-        int zz = 0;
-        if (DIM == 3) {
-            zz = cz + r / 3 - 1;
-            zz = zz < 0 ? zz + nc : (zz >= nc ? zz - nc : zz);
+    for (int dz = (DIM == 3 ? -1 : 0); dz <= (DIM == 3 ? 1 : 0); ++dz) {
+        int zz = cz + dz;
+        zz = zz < 0 ? zz + nc : (zz >= nc ? zz - nc : zz);
+#pragma unroll 1
+        for (int dy = -1; dy <= 1; ++dy) {
+            int yy = cy + dy;
+            yy = yy < 0 ? yy + nc : (yy >= nc ? yy - nc : yy);
+            const int rb = (zz * nc + yy) * nc;
+            cnt = scan_range<DIM, MODE>(i, xi, yi, zi, (int)cs1[rb + ax1], (int)cs1[rb + bx1], s.p, r2s, row, cap, cnt);
+            if (bx2 > ax2)
+                cnt = scan_range<DIM, MODE>(i, xi, yi, zi, (int)cs1[rb + ax2], (int)cs1[rb + bx2], s.p, r2s, row, cap, cnt);
         }
-        const int rb = (zz * nc + yy) * nc;
-        // the three x-cells of a row are contiguous in the sorted numbering except across the wrap
-        int a1, b1, a2 = 0, b2 = 0;
-        if (cx == 0) {
-            a1 = rb + nc - 1; b1 = rb + nc; a2 = rb; b2 = rb + 2;
-        } else if (cx == nc - 1) {
-            a1 = rb + nc - 2; b1 = rb + nc; a2 = rb; b2 = rb + 1;
-        } else {
-            a1 = rb + cx - 1; b1 = rb + cx + 2;
-        }
-        cnt = scan_range<DIM, WRITE>(i, xi, yi, zi, (int)s.cs[a1], (int)s.cs[b1], s, r2lat, row, cnt);
-        if (b2 > a2) cnt = scan_range<DIM, WRITE>(i, xi, yi, zi, (int)s.cs[a2], (int)s.cs[b2], s, r2lat, row, cnt);
     }
     return cnt;
+}
+
+template <int DIM>
+__device__ __forceinline__ uint32_t k2_cell(uint32_t kx, uint32_t ky, uint32_t kz, uint32_t nc) {
+    const uint32_t cx = (kx * nc) >> POS_BITS, cy = (ky * nc) >> POS_BITS;
+    const uint32_t cz = DIM == 3 ? (kz * nc) >> POS_BITS : 0u;
+    return (cz * nc + cy) * nc + cx;
 }
 
 template <int DIM>
@@ -136,15 +172,16 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(cons
     __shared__ unsigned int s_maxdeg;
     const int N = a.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     K2Smem s;
-    s.px = reinterpret_cast<uint32_t *>(smem_raw);
-    s.py = s.px + N;
-    s.pz = s.py + N;
+    s.p = reinterpret_cast<uint4 *>(smem_raw);
     s.tmp = reinterpret_cast<uint64_t *>(smem_raw + k2_o_tmp(N));
     s.off = reinterpret_cast<uint32_t *>(s.tmp);
     s.cs = reinterpret_cast<uint32_t *>(smem_raw + k2_o_cs(N));
+    s.seg = reinterpret_cast<uint16_t *>(smem_raw + k2_o_seg(N));
+    s.rk = reinterpret_cast<uint16_t *>(smem_raw + k2_o_rk(N));
+    uint16_t *stage = a.stage + (size_t)blockIdx.x * (size_t)N * (size_t)a.stage_cap;
 
     for (;;) {
-        __syncthreads();                          // everyone is done with s_ticket / s_base of the previous ticket
+        __syncthreads();                          // everyone is done with the shared scalars of the previous ticket
         if (tid == 0) {
             s_ticket = (long long)atomicAdd(a.ctr + CTR_K2_TICKET, 1ULL);
             s_maxdeg = 0u;
@@ -161,71 +198,70 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(cons
         int ncell = nc;
 #pragma unroll
         for (int d = 1; d < DIM; ++d) ncell *= nc;
+        // 2^22 r2lat, saturated at the largest possible sum of squares
         const unsigned long long r2lat = reach2_lattice(a.L, reach);
+        const unsigned long long r2s = r2lat >= (3ULL << 40) ? (3ULL << 62) : (r2lat << 22);
+        const int cap = min(a.stage_cap, k2_stage_cap(N, DIM, a.L, reach));
 
-        // ---- positions (all threads) and particles per cell (count of cell c kept at cs[c+1])
-        for (int c = tid; c <= ncell; c += K2_THREADS) s.cs[c] = 0u;
+        // ---- 1. positions, cell counts (kept at cs[c+2]) and arrival ranks
+        for (int c = tid; c < ncell + 2; c += K2_THREADS) s.cs[c] = 0u;
         __syncthreads();
         for (int i = tid; i < N; i += K2_THREADS) {
             const u32x4 r = philox4x32_10((uint32_t)i, STREAM_POSITIONS, rep, pidx, a.seed_lo, a.seed_hi);
             const uint32_t kx = r.x >> (32 - POS_BITS), ky = r.y >> (32 - POS_BITS);
             const uint32_t kz = DIM == 3 ? r.z >> (32 - POS_BITS) : 0u;
             s.tmp[i] = (uint64_t)kx | ((uint64_t)ky << POS_BITS) | ((uint64_t)kz << (2 * POS_BITS));
-            const uint32_t cell = (((kz * (uint32_t)nc) >> POS_BITS) * (uint32_t)nc + ((ky * (uint32_t)nc) >> POS_BITS)) *
-                                      (uint32_t)nc + ((kx * (uint32_t)nc) >> POS_BITS);
-            atomicAdd(&s.cs[cell + 1], 1u);
+            if (nc >= 3) s.rk[i] = (uint16_t)atomicAdd(&s.cs[k2_cell<DIM>(kx, ky, kz, (uint32_t)nc) + 2], 1u);
         }
         __syncthreads();
-        if (warp == 0) {
-            // exclusive scan kept one slot up: cs[c+1] = first sorted index of cell c (the running fill
-            // pointer of the scatter below, which leaves cs[c] = first index of cell c, cs[ncell] = N)
+        // ---- 2. cell starts: cs[c+1] = first sorted index of cell c (inclusive scan of the counts one slot up)
+        if (warp == 0 && nc >= 3) {
             const int per = (ncell + 31) >> 5;
             const int b = lane * per, e = min(b + per, ncell);
             int sum = 0;
-            for (int c = b; c < e; ++c) sum += (int)s.cs[c + 1];
+            for (int c = b; c < e; ++c) sum += (int)s.cs[c + 2];
             int run = warp_incl_scan(sum, lane, 32) - sum;
             for (int c = b; c < e; ++c) {
-                const int v = (int)s.cs[c + 1];
-                s.cs[c + 1] = (uint32_t)run;
-                run += v;
-            }
-            __syncwarp();
-            // stable scatter into cell order, 32 particles at a time in generation order
-            for (int base = 0; base < N; base += 32) {
-                const int i = base + lane;
-                uint32_t cell = 0x10000u + (uint32_t)lane;
-                uint32_t kx = 0, ky = 0, kz = 0;
-                if (i < N) {
-                    const uint64_t pk = s.tmp[i];
-                    kx = (uint32_t)pk & POS_MASK;
-                    ky = (uint32_t)(pk >> POS_BITS) & POS_MASK;
-                    kz = (uint32_t)(pk >> (2 * POS_BITS)) & POS_MASK;
-                    cell = (((kz * (uint32_t)nc) >> POS_BITS) * (uint32_t)nc + ((ky * (uint32_t)nc) >> POS_BITS)) *
-                               (uint32_t)nc + ((kx * (uint32_t)nc) >> POS_BITS);
-                }
-                const uint32_t mask = __match_any_sync(FULL, cell);
-                if (i < N) {
-                    const int dst = (int)s.cs[cell + 1] + __popc(mask & lanemask_lt());
-                    s.px[dst] = kx << 11;
-                    s.py[dst] = ky << 11;
-                    if (DIM == 3) s.pz[dst] = kz << 11;
-                }
-                __syncwarp();
-                if (i < N && (__ffs(mask) - 1) == lane) s.cs[cell + 1] += (uint32_t)__popc(mask);
-                __syncwarp();
+                run += (int)s.cs[c + 2];
+                s.cs[c + 2] = (uint32_t)run;
             }
         }
         __syncthreads();
-        // ---- pass A: degrees (tmp is dead: off aliases it)
+        // ---- 3. stable placement: group original indices by cell, then rank inside the cell by original index
+        if (nc >= 3) {
+            for (int i = tid; i < N; i += K2_THREADS) {
+                const uint64_t pk = s.tmp[i];
+                const uint32_t c = k2_cell<DIM>((uint32_t)pk & POS_MASK, (uint32_t)(pk >> POS_BITS) & POS_MASK,
+                                                (uint32_t)(pk >> (2 * POS_BITS)) & POS_MASK, (uint32_t)nc);
+                s.seg[s.cs[c + 1] + s.rk[i]] = (uint16_t)i;
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < N; i += K2_THREADS) {
+            const uint64_t pk = s.tmp[i];
+            const uint32_t kx = (uint32_t)pk & POS_MASK, ky = (uint32_t)(pk >> POS_BITS) & POS_MASK;
+            const uint32_t kz = (uint32_t)(pk >> (2 * POS_BITS)) & POS_MASK;
+            int dst = i;
+            if (nc >= 3) {
+                const uint32_t c = k2_cell<DIM>(kx, ky, kz, (uint32_t)nc);
+                const int st = (int)s.cs[c + 1], en = (int)s.cs[c + 2];
+                dst = st;
+                for (int w = st; w < en; ++w) dst += (int)s.seg[w] < i ? 1 : 0;
+            }
+            s.p[dst] = make_uint4(kx << 11, ky << 11, kz << 11, (uint32_t)i);
+        }
+        __syncthreads();
+        // ---- 4. the distance pass (tmp is dead: off aliases it)
         unsigned int mydeg = 0u;
         for (int i = tid; i < N; i += K2_THREADS) {
-            const int c = particle_row<DIM, false>(i, N, nc, s, r2lat, nullptr);
+            const int c = particle_row<DIM, 0>(i, N, nc, s, r2s, stage + (size_t)i * (size_t)a.stage_cap, cap);
             s.off[i + 1] = (uint32_t)c;
             mydeg = max(mydeg, (unsigned int)c);
         }
         mydeg = __reduce_max_sync(FULL, mydeg);
         if (lane == 0) atomicMax(&s_maxdeg, mydeg);
         __syncthreads();
+        // ---- 5. offsets and the record
         if (warp == 0) {
             // inclusive scan of the degrees in place: off[0] = 0, off[i+1] = entries of particles 0..i
             const int per = (N + 31) >> 5;
@@ -261,15 +297,25 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(cons
         __syncthreads();
         const unsigned long long at = s_base;
         if (at == ~0ULL) continue;
-        // ---- pass B: the record
+        // ---- 6. the record: offsets, then the staged rows compacted (or recomputed when a row overflowed its stride)
         uint32_t *goff = reinterpret_cast<uint32_t *>(a.arena + at);
         uint16_t *gnbr = reinterpret_cast<uint16_t *>(a.arena + at + (((size_t)(N + 1) * 4 + 15) & ~(size_t)15));
         for (int i = tid; i <= N; i += K2_THREADS) goff[i] = s.off[i];
-        for (int i = tid; i < N; i += K2_THREADS) particle_row<DIM, true>(i, N, nc, s, r2lat, gnbr + s.off[i]);
+        if ((int)s_maxdeg <= cap) {
+            for (int i = tid; i < N; i += K2_THREADS) {
+                const uint32_t o0 = s.off[i], dg = s.off[i + 1] - o0;
+                const uint16_t *src = stage + (size_t)i * (size_t)a.stage_cap;
+                for (uint32_t k = 0; k < dg; ++k) gnbr[o0 + k] = src[k];
+            }
+        } else {
+            for (int i = tid; i < N; i += K2_THREADS) particle_row<DIM, 1>(i, N, nc, s, r2s, gnbr + s.off[i], 0);
+        }
         if (a.spos_out && q == 0) {
-            for (int i = tid; i < N; i += K2_THREADS)
-                a.spos_out[i] = (uint64_t)(s.px[i] >> 11) | ((uint64_t)(s.py[i] >> 11) << POS_BITS) |
-                                (DIM == 3 ? (uint64_t)(s.pz[i] >> 11) << (2 * POS_BITS) : 0ULL);
+            for (int i = tid; i < N; i += K2_THREADS) {
+                const uint4 c = s.p[i];
+                a.spos_out[i] = (uint64_t)(c.x >> 11) | ((uint64_t)(c.y >> 11) << POS_BITS) |
+                                (DIM == 3 ? (uint64_t)(c.z >> 11) << (2 * POS_BITS) : 0ULL);
+            }
         }
     }
 }
@@ -966,6 +1012,7 @@ cudaError_t dispatch_traj(int wide_sn, int wide_off, F &&f) {
 }  // namespace
 
 int table_smem_bytes(int N) { return k2_bytes(N); }
+int table_stage_cap(int N, int DIM, double L, double reach) { return k2_stage_cap(N, DIM, L, reach); }
 
 int table_ctas_per_sm(int N, int DIM) {
     int nb = 0;

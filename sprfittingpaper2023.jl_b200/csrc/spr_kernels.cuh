@@ -39,6 +39,8 @@ struct TableArgs {                      // K2: spr_table_kernel
     unsigned long long arena_bytes;
     unsigned long long *desc;           // [ntickets]
     long long *defer_list;              // [ntickets]
+    uint16_t *stage;                    // [nblocks][N][stage_cap] staging rows of the distance pass
+    int stage_cap;                      // entries per staging row (>= the stride any trajectory of the launch uses)
     uint64_t *spos_out;                 // test hook: packed sorted lattice positions of local ticket 0, or nullptr
 };
 
@@ -89,6 +91,7 @@ inline size_t record_bytes(int N, unsigned long long entries) {
 // K2
 int table_smem_bytes(int N);
 int table_ctas_per_sm(int N, int DIM);
+int table_stage_cap(int N, int DIM, double L, double reach);   // staging stride for one reach value
 cudaError_t launch_table(const TableArgs &a, int DIM, int nblocks, cudaStream_t st);
 constexpr int K2_THREADS = 256;
 

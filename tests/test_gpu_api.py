@@ -236,6 +236,16 @@ def test_arena_chunks_and_deferred_tables(engine, oracle_libs):
         assert launches > base_launches, env
         for k in ("sum", "sumsq", "n_events", "n_used"):
             assert np.array_equal(out[k], ref[k]), (k, env)
+    # a staging stride smaller than the largest degree makes the table kernel redo its distance pass
+    os.environ["SPRB200_STAGE_CAP"] = "8"
+    try:
+        eng4 = sprb200.Engine(0)
+        out = eng4.simulate(sim, pts, run)
+        eng4.close()
+    finally:
+        del os.environ["SPRB200_STAGE_CAP"]
+    for k in ("sum", "sumsq", "n_events", "n_used"):
+        assert np.array_equal(out[k], ref[k]), (k, "stage cap")
     # an arena smaller than a single table is an error, not a hang
     os.environ["SPRB200_TABLE_BYTES"] = str(70 * 1024)
     try:
