@@ -874,20 +874,29 @@ __global__ void fixed_graph_fill_kernel(const double *locs, int N, int DIM, doub
 // ------------------------------------------------------------------------------------------------
 // K3: replicate reduction (fixed count) -- sum and sum of squares per (slot, bin) over nrep curves
 // ------------------------------------------------------------------------------------------------
-__global__ void reduce_fixed_kernel(const uint16_t *__restrict__ curve, int repstride, int nrep, int T,
+__global__ void reduce_fixed_kernel(const uint16_t *__restrict__ curve, int repstride, int nrep, int T, int nsplit,
                                     long long *__restrict__ sum, unsigned long long *__restrict__ sumsq) {
     const int slot = blockIdx.x;
+    // blockIdx.y takes a contiguous share of the replicates (nsplit > 1 only when one point has very many
+    // replicates; integer sums, so the atomic accumulation stays bit-exact)
+    const int per = (nrep + nsplit - 1) / nsplit;
+    const int r0 = blockIdx.y * per, r1 = min(r0 + per, nrep);
     const uint16_t *base = curve + (size_t)slot * repstride * T;
     for (int s = threadIdx.x; s < T; s += blockDim.x) {
         long long S = 0;
         unsigned long long Q = 0;
-        for (int r = 0; r < nrep; ++r) {
+        for (int r = r0; r < r1; ++r) {
             const unsigned int v = base[(size_t)r * T + s];
             S += v;
             Q += (unsigned long long)v * v;
         }
-        sum[(size_t)slot * T + s] = S;
-        sumsq[(size_t)slot * T + s] = Q;
+        if (nsplit == 1) {
+            sum[(size_t)slot * T + s] = S;
+            sumsq[(size_t)slot * T + s] = Q;
+        } else if (r1 > r0) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(sum) + (size_t)slot * T + s, (unsigned long long)S);
+            atomicAdd(sumsq + (size_t)slot * T + s, Q);
+        }
     }
 }
 
@@ -1108,7 +1117,20 @@ cudaError_t launch_fixed_graph(const double *d_locs, int N, int DIM, double L, d
 cudaError_t launch_reduce_fixed(const uint16_t *curve, int nslots, int repstride, int nrep, int T, long long *sum,
                                 unsigned long long *sumsq, cudaStream_t st) {
     if (nslots <= 0) return cudaSuccess;
-    reduce_fixed_kernel<<<nslots, 128, 0, st>>>(curve, repstride, nrep, T, sum, sumsq);
+    // enough blocks to fill the GPU even for a single point with many replicates
+    int nsplit = 1;
+    if ((long long)nslots < 1024 && nrep > 256) {
+        nsplit = (nrep + 255) / 256;
+        const int want = (1024 + nslots - 1) / nslots;
+        if (nsplit > want) nsplit = want;
+        if (nsplit > 65535) nsplit = 65535;
+    }
+    if (nsplit > 1) {
+        cudaError_t e = cudaMemsetAsync(sum, 0, sizeof(long long) * (size_t)nslots * T, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(sumsq, 0, sizeof(unsigned long long) * (size_t)nslots * T, st);
+        if (e != cudaSuccess) return e;
+    }
+    reduce_fixed_kernel<<<dim3((unsigned)nslots, (unsigned)nsplit), 128, 0, st>>>(curve, repstride, nrep, T, nsplit, sum, sumsq);
     return cudaGetLastError();
 }
 

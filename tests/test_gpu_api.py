@@ -58,6 +58,24 @@ def test_bit_exact_across_gpu_counts_and_batching(engine, built_lib):
     assert t4.tobytes() != table.tobytes()
 
 
+def test_many_replicates_of_one_point_reduce_exactly(engine):
+    """one point with many replicates (the reference's default use: run_spr_sim! with nsims = 1000): the
+    replicate reduction is split over several blocks with integer atomics and must equal the sums of
+    the raw curves"""
+    import sprb200
+    from sprb200 import _lib
+    tsave = np.linspace(0.0, 60.0, 31)
+    sim = sprb200.SimSpec(300, 3, _lib.domain_length(300, 3), 60.0, 25.0, tsave)
+    pt = [[0.05, 0.05, 0.8, 25.0]]
+    run = sprb200.make_run(nsims=1500, seed=77)
+    out = engine.simulate(sim, pt, run)
+    B, C, nev = engine.simulate_raw(sim, pt, run)
+    x = (B[0].astype(np.int64) + C[0].astype(np.int64))
+    assert np.array_equal(out["sum"][0], x.sum(axis=0))
+    assert np.array_equal(out["sumsq"][0].astype(np.int64), (x * x).sum(axis=0))
+    assert int(out["n_events"][0]) == int(nev[0]) and int(out["n_used"][0]) == 1500
+
+
 def test_variance_build_is_partition_independent(engine):
     import sprb200
     grid, sim, P = small_setup(size=(3, 2, 2, 3), T=21)
