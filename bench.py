@@ -132,13 +132,13 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------
 def cpu_sample(ncores, seed):
-    """Bounded sample of the same workload for the CPU legs: 4 points per host thread drawn uniformly
-    (seeded) from the 10^4-point C2 grid, 100 replicates each (about 10-30 s on all cores)."""
+    """Bounded sample of the same workload for the CPU legs: 12 points per host thread drawn uniformly
+    (seeded) from the 10^4-point C2 grid, 100 replicates each (about 10-20 s on all cores)."""
     from sprb200 import _lib
     grid = _lib.make_grid(RANGES["logkon"], RANGES["logkoff"], RANGES["logkonb"], RANGES["reach"],
                           NK + (NREACH_PER_GPU,))
     P = NK[0] * NK[1] * NK[2] * NREACH_PER_GPU
-    npts = int(min(P, max(16, 4 * ncores)))
+    npts = int(min(P, max(16, 12 * ncores)))
     rng = np.random.default_rng(seed)
     idx = np.sort(rng.choice(P, size=npts, replace=False)) + 1
     import ctypes as C
@@ -243,6 +243,8 @@ def main():
 
     launches = [0]
     build_ms = [0.0]
+    traj_ms = [0.0]
+    table_ms = [0.0]
     events_step = [0]
 
     def step(seed):
@@ -251,6 +253,8 @@ def main():
         st = eng.stats()
         launches[0] += st["kernel_launches"] + 1
         build_ms[0] += st["device_ms"]
+        traj_ms[0] += st["traj_ms"]
+        table_ms[0] += st["table_ms"]
         events_step[0] += st["events"]
         if world > 1:
             dist.all_gather_into_tensor(all_rows, rows)
@@ -259,7 +263,7 @@ def main():
 
     for w in range(W):
         step(SEED + 100 + w)
-    launches[0] = 0; build_ms[0] = 0.0; events_step[0] = 0
+    launches[0] = 0; build_ms[0] = 0.0; traj_ms[0] = 0.0; table_ms[0] = 0.0; events_step[0] = 0
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -277,12 +281,12 @@ def main():
     nev_host = nev_d.cpu().numpy().astype(np.float64)          # last step's per-point events (this rank)
 
     # whole-job numbers: max time over ranks, events summed over ranks
-    tms = torch.tensor([ms, build_ms[0]], dtype=torch.float64, device=dev)
+    tms = torch.tensor([ms, build_ms[0], traj_ms[0], table_ms[0]], dtype=torch.float64, device=dev)
     tev = torch.tensor([float(events_step[0]), float(launches[0])], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tev, op=dist.ReduceOp.SUM)
-    ms_total, build_ms_total = float(tms[0]), float(tms[1])
+    ms_total, build_ms_total, traj_ms_total, table_ms_total = float(tms[0]), float(tms[1]), float(tms[2]), float(tms[3])
     ev_total, launches_total = float(tev[0]), int(tev[1])
     value = ev_total / (ms_total * 1e-3)
     traj_total = count * NREP * world * K
@@ -322,7 +326,7 @@ def main():
         deg = np.array([mean_degree(r, L) for r in reach_of])
         balg = 4.0 * NPART + 1.9 * (10.0 + 11.0 * deg)
         balg_mean = float((balg * nev_host).sum() / max(nev_host.sum(), 1.0))
-        ev_rate_kernel = ev_total / world / (build_ms_total * 1e-3)        # per GPU, kernel time only
+        ev_rate_kernel = ev_total / world / (traj_ms_total * 1e-3)         # per GPU, trajectory kernel (K1) time only
         smem_peak = SMEM_B_PER_CLK * f_hz / 1e9
         smem_ach = ev_rate_kernel * balg_mean / 1e9
         issue_peak = ISSUE_PER_CLK * f_hz
@@ -332,8 +336,11 @@ def main():
             "note": "path is neither HBM- nor tensor-bound (SURVEY.md 8d): achieved = events/s/GPU x flat-scan "
                     "algorithmic shared-memory bytes per event (%.0f B, events-weighted 4N + 1.9(10+11deg)); peak = "
                     "148 SM x 128 B/clk x measured SM clock %.0f MHz (fallback formula of SURVEY.md 8d, not in "
-                    "MEASURED_PEAKS.json); kernel time = CUDA events on the library's launch stream" % (balg_mean, f_mhz),
+                    "MEASURED_PEAKS.json); kernel time = CUDA events around the K1 launches on the library's stream, "
+                    "live in this run" % (balg_mean, f_mhz),
             "events_per_sec_per_gpu_kernel": ev_rate_kernel,
+            "kernel_ms_per_step": {"spr_traj_kernel": traj_ms_total / K, "spr_table_kernel": table_ms_total / K,
+                                   "build_total": build_ms_total / K},
         }
         roofline_issue = {
             "bound": "issue", "achieved": ev_rate_kernel * I_ALG, "peak": issue_peak, "unit": "warp-inst/s",

@@ -2,7 +2,8 @@
 """Summarise an .ncu-rep: headline counters + instructions/stall samples per CUDA source line."""
 import csv, subprocess, sys, io
 rep = sys.argv[1]; events = float(sys.argv[2]) if len(sys.argv) > 2 else None; top = int(sys.argv[3]) if len(sys.argv) > 3 else 45
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+kf = ["-k", "regex:" + sys.argv[4]] if len(sys.argv) > 4 else []
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + kf, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 d = dict(zip(hdr, vals))
@@ -23,7 +24,7 @@ for k, v in d.items():
 inst = float(d["sm__inst_executed.sum.per_cycle_elapsed"].replace(",", "")) * float(d["sm__cycles_elapsed.avg"].replace(",", ""))
 print("warp-instructions executed: %.4g" % inst)
 if events: print("warp-instructions per event: %.1f ; smem wavefronts per event %.1f" % (inst / events, float(d["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"].replace(",","")) / events))
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + kf, capture_output=True, text=True).stdout
 cur = None; data = []; tot = 0; tots = 0
 for r in csv.reader(io.StringIO(src)):
     if len(r) >= 2 and r[0] == "File Path": cur = r[1].split("/")[-1]; continue
