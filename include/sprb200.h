@@ -131,6 +131,13 @@ int sprb200_last_stats(sprb200_handle h, uint64_t *trajectories, uint64_t *event
  * kernel (K1), summed over their launches (CUDA events on the handle's stream). */
 int sprb200_last_kernel_ms(sprb200_handle h, double *table_ms, double *traj_ms);
 
+/* Shared-memory plan of the trajectory kernel on a B200 for N particles (no device needed):
+ * out[0] = bytes of shared memory per trajectory, out[1] = trajectories (warps) per CTA, out[2] = CTAs per
+ * SM, out[3] = bytes of shared memory of one table-build CTA.  wide_state / wide_offsets select the
+ * 32-bit state words (a degree above 127) / offsets (more than 65,535 table entries).
+ * SPRB200_ERR_TOO_LARGE when one trajectory does not fit. */
+int sprb200_traj_layout(int32_t N, int32_t wide_state, int32_t wide_offsets, int32_t out[4]);
+
 /* ---- helpers --------------------------------------------------------------------------- */
 /* L = (N / agc)^(1/DIM), agc = 6.02214076e-7*antigenconcen if convert_units (parameters.jl:138-139) */
 double sprb200_domain_length(int32_t N, int32_t DIM, double antigenconcen, int32_t convert_units);

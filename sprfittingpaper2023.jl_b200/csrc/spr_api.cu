@@ -726,6 +726,18 @@ int sprb200_last_kernel_ms(sprb200_handle h, double *table_ms, double *traj_ms) 
     return SPRB200_OK;
 }
 
+int sprb200_traj_layout(int32_t N, int32_t wide_state, int32_t wide_offsets, int32_t out[4]) {
+    if (!out || N < 1 || N > 65535) return SPRB200_ERR_BAD_ARG;
+    TrajLayout lay;
+    // B200: 227 KB of dynamic shared memory per CTA, 228 KB per SM
+    const bool ok = make_traj_layout(N, wide_state != 0, wide_offsets != 0, 227 * 1024, 228 * 1024, &lay);
+    out[0] = lay.slice;
+    out[1] = lay.wpc;
+    out[2] = lay.cta_per_sm;
+    out[3] = table_smem_bytes(N);
+    return ok ? SPRB200_OK : SPRB200_ERR_TOO_LARGE;
+}
+
 double sprb200_domain_length(int32_t N, int32_t DIM, double antigenconcen, int32_t convert_units) {
     const double agc = convert_units ? 6.02214076e-7 * antigenconcen : antigenconcen;
     return std::pow((double)N / agc, 1.0 / (double)DIM);

@@ -16,7 +16,7 @@ OBS_TOTAL_BOUND, OBS_TOTAL_A = 0, 1
 
 EXPORTS = [
     "sprb200_abi_version", "sprb200_create", "sprb200_destroy", "sprb200_last_error", "sprb200_last_stats",
-    "sprb200_last_kernel_ms",
+    "sprb200_last_kernel_ms", "sprb200_traj_layout",
     "sprb200_domain_length", "sprb200_grid_value", "sprb200_grid_point", "sprb200_simulate",
     "sprb200_simulate_raw", "sprb200_neighbor_table", "sprb200_build_slice", "sprb200_build_table",
     "sprb200_merge_slice", "sprb200_build_slice_device", "sprb200_scatter_table_device",
@@ -80,6 +80,8 @@ def load():
     L.sprb200_last_error.argtypes = [vp]
     L.sprb200_last_stats.restype = C.c_int
     L.sprb200_last_stats.argtypes = [vp, P(u64), P(u64), P(u64), P(dbl)]
+    L.sprb200_traj_layout.restype = C.c_int
+    L.sprb200_traj_layout.argtypes = [i32, i32, i32, P(i32)]
     L.sprb200_last_kernel_ms.restype = C.c_int
     L.sprb200_last_kernel_ms.argtypes = [vp, P(dbl), P(dbl)]
     L.sprb200_domain_length.restype = dbl
@@ -119,6 +121,15 @@ def load():
 
 def _ptr(a, ct):
     return a.ctypes.data_as(C.POINTER(ct)) if a is not None else None
+
+
+def traj_layout(N, wide_state=False, wide_offsets=False):
+    """(bytes per trajectory, trajectories per CTA, CTAs per SM, bytes of a table-build CTA) on a B200"""
+    out = (C.c_int32 * 4)()
+    rc = load().sprb200_traj_layout(int(N), int(bool(wide_state)), int(bool(wide_offsets)), out)
+    if rc != OK:
+        raise SprB200Error(rc, "per-trajectory state for N=%d does not fit in shared memory" % N)
+    return tuple(out)
 
 
 class SimSpec:
