@@ -23,6 +23,8 @@
  * merge_surrogate_slices (column scatter) :302-318           | sprb200_merge_slice
  * SimParams(...) L from antigen concentration                | sprb200_domain_length
  *   src/parameters.jl:124-150, src/utils.jl:10               |
+ * surrogate_sprdata_error(optpars, pars)                      | sprb200_surrogate_load,
+ *   src/fitting.jl:38-91 (5-D interpolation + l2 loss)       | sprb200_fit_loss (whole population)
  * (none: the reference is single-process)                    | sprb200_build_slice_device,
  *                                                            | sprb200_scatter_table_device:
  *                                                            | device-resident slabs for the
@@ -208,6 +210,27 @@ int sprb200_build_indices(sprb200_handle h, const SprGrid *grid, const SprSim *s
 /* d_table[s*P + idx[k]-1] = d_rows[k*T + s] for a host index list (after the NCCL gather). */
 int sprb200_scatter_rows_device(sprb200_handle h, const double *d_rows, const int64_t *idx,
                                 int64_t count, int32_t T, int64_t P, double *d_table);
+
+/* ---- the consumer of the table: surrogate_sprdata_error (src/fitting.jl:38-91) ------------------- */
+/* Mirror of AlignedData (src/spr_data.jl:9-18) in concatenated form. */
+typedef struct {
+    int32_t nconc;                 /* number of antibody concentrations (curves) */
+    const int32_t *npts;           /* [nconc] samples per curve */
+    const double *times;           /* [sum npts] times[i] of every curve, concatenated */
+    const double *values;          /* [sum npts] refdata[i], concatenated */
+    const double *antibodyconcens; /* [nconc]; the first one is the reference concentration (:66) */
+} SprAligned;
+/* Keeps a surrogate resident on the device: `table` is the FirstMoment array (n1,n2,n3,n4,T) column-major
+ * (what sprb200_build_table writes) on the host, or on the device when table_on_device != 0; tsave must be
+ * uniform from t_first to t_last (surrogate.jl:96-108 assumes the same). */
+int sprb200_surrogate_load(sprb200_handle h, const SprGrid *grid, int32_t T, double t_first, double t_last,
+                           const double *table, int32_t table_on_device);
+/* loss[k] = sum over curves j and samples i of (10^p5 * itp(q1_j, q2, q3, q4, s_i) - refdata[j][i])^2 for
+ * candidate k = optpars[5k .. 5k+4] = [logkon, logkoff, logkonb, reach, logCP]; itp is the 5-D
+ * multilinear interpolation of the loaded table at fractional 1-based indices (surrogate.jl:66-70),
+ * logkon is shifted by log10(abc_j / abc_1) per curve.  A candidate or sample outside the table gives
+ * +Inf (Interpolations.jl throws BoundsError there).  Host pointers; blocking. */
+int sprb200_fit_loss(sprb200_handle h, const SprAligned *data, const double *optpars, int64_t npop, double *loss);
 
 #ifdef __cplusplus
 }

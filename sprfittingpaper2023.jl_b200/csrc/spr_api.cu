@@ -60,7 +60,7 @@ struct sprb200_ctx {
     std::string err;
     // arenas
     DevBuf tsave, pts, pidx, order, curve, curve2, sum, sumsq, nused, nevents, nscanned, nstar, active, counters,
-        rows, locs, goff, gnbr, misc, table, arena, desc, defer, tickets, slotrec, stage;
+        rows, locs, goff, gnbr, misc, table, arena, desc, defer, tickets, slotrec, stage, sur, fitdata, fitpars, fitloss;
     // stats of the last call
     uint64_t st_traj = 0, st_events = 0, st_launches = 0;
     double st_ms = 0.0, st_table_ms = 0.0, st_traj_ms = 0.0;
@@ -78,6 +78,11 @@ struct sprb200_ctx {
     size_t table_budget = (size_t)16 << 30;   // SPRB200_TABLE_BYTES: neighbour-table arena (K2 -> K1)
     double est_scale = 1.0;   // SPRB200_CAP_SCALE (test hook): scales the a-priori table size used for chunking
     int max_warps = 0;        // SPRB200_MAX_WARPS (experiment hook): cap on resident trajectories per SM
+    // resident surrogate (sprb200_surrogate_load)
+    SprGrid sur_grid = {};
+    int sur_T = 0;
+    double sur_t0 = 0.0, sur_t1 = 0.0;
+    long long sur_P = 0;
     int stage_cap_override = 0;   // SPRB200_STAGE_CAP (test hook): staging stride of K2's distance pass
     int k1_variant = 5;       // SPRB200_K1_VARIANT (experiment hook): trajectory-kernel instantiation (4 or 5)
 };
@@ -696,7 +701,7 @@ void sprb200_destroy(sprb200_handle h) {
     }
     DevBuf *bufs[] = {&h->tsave, &h->pts, &h->pidx, &h->order, &h->curve, &h->curve2, &h->sum, &h->sumsq, &h->nused,
                       &h->nevents, &h->nscanned, &h->nstar, &h->active, &h->counters, &h->rows, &h->locs,
-                      &h->goff, &h->gnbr, &h->misc, &h->table, &h->arena, &h->desc, &h->defer, &h->tickets, &h->slotrec, &h->stage};
+                      &h->goff, &h->gnbr, &h->misc, &h->table, &h->arena, &h->desc, &h->defer, &h->tickets, &h->slotrec, &h->stage, &h->sur, &h->fitdata, &h->fitpars, &h->fitloss};
     for (DevBuf *b : bufs) b->release();
     for (int s = 0; s < NSTREAM; ++s) {
         if (h->stream[s]) cudaStreamDestroy(h->stream[s]);
@@ -1003,6 +1008,77 @@ int sprb200_scatter_rows_device(sprb200_handle h, const double *d_rows, const in
     CUDA_TRY(h, cudaMemcpyAsync(h->misc.p, idx, sizeof(int64_t) * (size_t)count, cudaMemcpyHostToDevice, h->stream[0]));
     CUDA_TRY(h, launch_scatter_idx(d_rows, h->misc.as<long long>(), count, T, P, d_table, h->stream[0]));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream[0]));
+    return SPRB200_OK;
+}
+
+int sprb200_surrogate_load(sprb200_handle h, const SprGrid *grid, int32_t T, double t_first, double t_last,
+                           const double *table, int32_t table_on_device) {
+    if (!h) return SPRB200_ERR_BAD_ARG;
+    int64_t P = 0;
+    if (grid_total(grid, &P)) return fail(h, SPRB200_ERR_BAD_ARG, "bad grid");
+    if (!table || T < 1 || !std::isfinite(t_first) || !std::isfinite(t_last) || (T > 1 && !(t_last > t_first)))
+        return fail(h, SPRB200_ERR_BAD_ARG, "bad surrogate arguments");
+    for (int k = 0; k < 4; ++k)
+        if (!std::isfinite(grid->lo[k]) || !std::isfinite(grid->hi[k]) || (grid->n[k] > 1 && !(grid->hi[k] > grid->lo[k])))
+            return fail(h, SPRB200_ERR_BAD_ARG, "surrogate axis ranges must be finite and increasing");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t bytes = sizeof(double) * (size_t)P * (size_t)T;
+    CUDA_TRY(h, h->sur.ensure(bytes));
+    CUDA_TRY(h, cudaMemcpyAsync(h->sur.p, table, bytes, table_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                h->stream[0]));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream[0]));
+    h->sur_grid = *grid;
+    h->sur_T = T;
+    h->sur_t0 = t_first;
+    h->sur_t1 = t_last;
+    h->sur_P = P;
+    return SPRB200_OK;
+}
+
+int sprb200_fit_loss(sprb200_handle h, const SprAligned *data, const double *optpars, int64_t npop, double *loss) {
+    if (!h) return SPRB200_ERR_BAD_ARG;
+    if (h->sur_T < 1) return fail(h, SPRB200_ERR_BAD_ARG, "no surrogate loaded (sprb200_surrogate_load)");
+    if (!data || data->nconc < 1 || !data->npts || !data->times || !data->values || !data->antibodyconcens)
+        return fail(h, SPRB200_ERR_BAD_ARG, "bad aligned data");
+    if (!optpars || !loss || npop < 1 || npop > 0x7fffffffLL) return fail(h, SPRB200_ERR_BAD_ARG, "bad population arguments");
+    long long ns = 0;
+    for (int j = 0; j < data->nconc; ++j) {
+        if (data->npts[j] < 0) return fail(h, SPRB200_ERR_BAD_ARG, "negative sample count");
+        if (!(data->antibodyconcens[j] > 0.0)) return fail(h, SPRB200_ERR_BAD_ARG, "antibody concentrations must be positive");
+        ns += data->npts[j];
+    }
+    cudaStream_t s0 = h->stream[0];
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    // packed upload: times | values | abcs | npts
+    const size_t o_val = sizeof(double) * (size_t)ns, o_abc = 2 * o_val, o_npts = o_abc + sizeof(double) * data->nconc;
+    const size_t total = o_npts + sizeof(int) * data->nconc;
+    std::vector<unsigned char> pack(total + 8);
+    if (ns) {
+        std::memcpy(pack.data(), data->times, o_val);
+        std::memcpy(pack.data() + o_val, data->values, o_val);
+    }
+    std::memcpy(pack.data() + o_abc, data->antibodyconcens, sizeof(double) * data->nconc);
+    for (int j = 0; j < data->nconc; ++j) reinterpret_cast<int *>(pack.data() + o_npts)[j] = data->npts[j];
+    CUDA_TRY(h, h->fitdata.ensure(total + 8));
+    CUDA_TRY(h, h->fitpars.ensure(sizeof(double) * 5 * (size_t)npop));
+    CUDA_TRY(h, h->fitloss.ensure(sizeof(double) * (size_t)npop));
+    CUDA_TRY(h, cudaMemcpyAsync(h->fitdata.p, pack.data(), total, cudaMemcpyHostToDevice, s0));
+    CUDA_TRY(h, cudaMemcpyAsync(h->fitpars.p, optpars, sizeof(double) * 5 * (size_t)npop, cudaMemcpyHostToDevice, s0));
+    FitArgs a{};
+    a.table = h->sur.as<double>();
+    a.P = h->sur_P;
+    for (int k = 0; k < 4; ++k) { a.n[k] = h->sur_grid.n[k]; a.lo[k] = h->sur_grid.lo[k]; a.hi[k] = h->sur_grid.hi[k]; }
+    a.T = h->sur_T; a.t_first = h->sur_t0; a.t_last = h->sur_t1;
+    a.nconc = data->nconc; a.nsamples = ns;
+    a.times = h->fitdata.as<double>();
+    a.values = reinterpret_cast<const double *>(h->fitdata.as<unsigned char>() + o_val);
+    a.abcs = reinterpret_cast<const double *>(h->fitdata.as<unsigned char>() + o_abc);
+    a.npts = reinterpret_cast<const int *>(h->fitdata.as<unsigned char>() + o_npts);
+    a.optpars = h->fitpars.as<double>();
+    a.loss = h->fitloss.as<double>();
+    CUDA_TRY(h, launch_fit_loss(a, npop, s0));
+    CUDA_TRY(h, cudaMemcpyAsync(loss, h->fitloss.p, sizeof(double) * (size_t)npop, cudaMemcpyDeviceToHost, s0));
+    CUDA_TRY(h, cudaStreamSynchronize(s0));
     return SPRB200_OK;
 }
 

@@ -988,6 +988,93 @@ __global__ void scatter_idx_kernel(const double *__restrict__ rows, const long l
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K5: the consumer of the table: surrogate_sprdata_error (/root/reference/src/fitting.jl:38-91) for a whole
+// optimiser population at once.  One CTA per candidate [logkon, logkoff, logkonb, reach, logCP]; each
+// thread takes samples (concentration j, time t) in a strided loop: 5-D multilinear interpolation of
+// the FirstMoment table at fractional 1-based indices (Interpolations.jl BSpline(Linear()),
+// surrogate.jl:66-70) = 32 gathers, squared residual against the data, fixed-order block reduction.
+// A candidate or time outside the table gives +Inf (Interpolations throws BoundsError there; the
+// reference keeps the optimiser inside with checkranges / rescale_logkon_max, fitting.jl:93-114).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool lut_index(double q, int n, int *i0, double *w) {
+    // fractional 1-based index q in [1, n] -> 0-based lower corner and weight of the upper corner
+    if (!(q >= 1.0 && q <= (double)n)) return false;
+    if (n == 1) { *i0 = 0; *w = 0.0; return true; }
+    int i = (int)floor(q);
+    if (i > n - 1) i = n - 1;
+    *i0 = i - 1;
+    *w = q - (double)i;
+    return true;
+}
+
+__global__ void __launch_bounds__(128) fit_loss_kernel(const FitArgs a) {
+    __shared__ double red[128];
+    __shared__ double cw[8];
+    __shared__ long long coff[8];
+    __shared__ int s_bad;
+    const int cand = blockIdx.x, tid = threadIdx.x;
+    const double *op = a.optpars + (size_t)cand * 5;
+    const long long n1 = a.n[0], n2 = a.n[1], n3 = a.n[2];
+    if (tid == 0) {
+        int i2, i3, i4;
+        double w2, w3, w4;
+        const double q2 = (op[1] - a.lo[1]) * (double)(a.n[1] - 1) / (a.hi[1] - a.lo[1]) + 1.0;
+        const double q3 = (op[2] - a.lo[2]) * (double)(a.n[2] - 1) / (a.hi[2] - a.lo[2]) + 1.0;
+        const double q4 = (op[3] - a.lo[3]) * (double)(a.n[3] - 1) / (a.hi[3] - a.lo[3]) + 1.0;
+        const bool ok = lut_index(q2, a.n[1], &i2, &w2) && lut_index(q3, a.n[2], &i3, &w3) && lut_index(q4, a.n[3], &i4, &w4);
+        s_bad = ok ? 0 : 1;
+        if (ok) {
+            for (int c = 0; c < 8; ++c) {
+                const int b2 = c & 1, b3 = (c >> 1) & 1, b4 = (c >> 2) & 1;
+                // an upper corner with zero weight may lie outside the table (q == n): clamp its index
+                const int j2 = min(i2 + b2, a.n[1] - 1), j3 = min(i3 + b3, a.n[2] - 1), j4 = min(i4 + b4, a.n[3] - 1);
+                cw[c] = (b2 ? w2 : 1.0 - w2) * (b3 ? w3 : 1.0 - w3) * (b4 ? w4 : 1.0 - w4);
+                coff[c] = n1 * ((long long)j2 + n2 * ((long long)j3 + n3 * (long long)j4));
+            }
+        }
+    }
+    __syncthreads();
+    double err = 0.0;
+    bool bad = s_bad != 0;
+    if (!bad) {
+        const double cp = pow(10.0, op[4]);
+        const double tspan = a.t_last - a.t_first;
+        int j = 0;
+        long long first = 0;          // index of the first sample of concentration j
+        for (long long k = tid; k < a.nsamples; k += blockDim.x) {
+            while (k >= first + a.npts[j]) { first += a.npts[j]; ++j; }
+            // rescale the on rate for the antibody concentration of this curve (fitting.jl:71)
+            const double logkon = op[0] + log10(a.abcs[j] / a.abcs[0]);
+            const double q1 = (logkon - a.lo[0]) * (double)(a.n[0] - 1) / (a.hi[0] - a.lo[0]) + 1.0;
+            const double sq = (a.times[k] - a.t_first) * (double)(a.T - 1) / tspan + 1.0;
+            int i1, is;
+            double w1, ws;
+            if (!lut_index(q1, a.n[0], &i1, &w1) || !lut_index(sq, a.T, &is, &ws)) { bad = true; break; }
+            const int i1b = min(i1 + 1, a.n[0] - 1), isb = min(is + 1, a.T - 1);
+            const double *t0 = a.table + (size_t)is * (size_t)a.P, *t1 = a.table + (size_t)isb * (size_t)a.P;
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const long long o = coff[c];
+                const double lo_t = (1.0 - w1) * t0[o + i1] + w1 * t0[o + i1b];
+                const double hi_t = (1.0 - w1) * t1[o + i1] + w1 * t1[o + i1b];
+                v += cw[c] * ((1.0 - ws) * lo_t + ws * hi_t);
+            }
+            const double r = cp * v - a.values[k];
+            err += r * r;
+        }
+    }
+    red[tid] = err;
+    if (bad) atomicExch(&s_bad, 1);
+    __syncthreads();
+    for (int st = 64; st > 0; st >>= 1) {
+        if (tid < st) red[tid] += red[tid + st];
+        __syncthreads();
+    }
+    if (tid == 0) a.loss[cand] = s_bad ? __longlong_as_double(0x7ff0000000000000LL) : red[0];
+}
+
 inline int align16(int x) { return (x + 15) & ~15; }
 
 template <int DIM>
@@ -1111,6 +1198,12 @@ cudaError_t launch_fixed_graph(const double *d_locs, int N, int DIM, double L, d
     } else {
         fixed_graph_fill_kernel<<<nb, 128, 0, st>>>(d_locs, N, DIM, L, reach2, d_off, d_nbr, nbr_cap);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fit_loss(const FitArgs &a, long long npop, cudaStream_t st) {
+    if (npop <= 0) return cudaSuccess;
+    fit_loss_kernel<<<(unsigned)npop, 128, 0, st>>>(a);
     return cudaGetLastError();
 }
 

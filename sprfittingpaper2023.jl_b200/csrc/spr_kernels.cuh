@@ -83,6 +83,22 @@ struct TrajArgs {                       // K1: spr_traj_kernel
     TrajLayout lay;
 };
 
+struct FitArgs {                        // K5: fit_loss_kernel
+    const double *table;                // FirstMoment [T][P] on the device
+    long long P;
+    int n[4], T;
+    double lo[4], hi[4];                // axis ranges (log10 kon', log10 koff, log10 konb, reach)
+    double t_first, t_last;             // tsave[1], tsave[end]
+    int nconc;
+    long long nsamples;
+    const int *npts;                    // [nconc]
+    const double *times, *values;       // [nsamples] concatenated per concentration
+    const double *abcs;                 // [nconc] antibody concentrations
+    const double *optpars;              // [npop][5]
+    double *loss;                       // [npop]
+};
+cudaError_t launch_fit_loss(const FitArgs &a, long long npop, cudaStream_t st);
+
 inline size_t align16z(size_t x) { return (x + 15) & ~(size_t)15; }
 inline size_t record_bytes(int N, unsigned long long entries) {
     return align16z(sizeof(uint32_t) * (size_t)(N + 1)) + align16z(sizeof(uint16_t) * (size_t)entries);

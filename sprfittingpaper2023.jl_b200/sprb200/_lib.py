@@ -16,7 +16,7 @@ OBS_TOTAL_BOUND, OBS_TOTAL_A = 0, 1
 
 EXPORTS = [
     "sprb200_abi_version", "sprb200_create", "sprb200_destroy", "sprb200_last_error", "sprb200_last_stats",
-    "sprb200_last_kernel_ms", "sprb200_traj_layout",
+    "sprb200_last_kernel_ms", "sprb200_traj_layout", "sprb200_surrogate_load", "sprb200_fit_loss",
     "sprb200_domain_length", "sprb200_grid_value", "sprb200_grid_point", "sprb200_simulate",
     "sprb200_simulate_raw", "sprb200_neighbor_table", "sprb200_build_slice", "sprb200_build_table",
     "sprb200_merge_slice", "sprb200_build_slice_device", "sprb200_scatter_table_device",
@@ -48,6 +48,11 @@ class SprOut(C.Structure):
 
 class SprGrid(C.Structure):
     _fields_ = [("lo", C.c_double * 4), ("hi", C.c_double * 4), ("n", C.c_int32 * 4)]
+
+
+class SprAligned(C.Structure):
+    _fields_ = [("nconc", C.c_int32), ("npts", C.POINTER(C.c_int32)), ("times", C.POINTER(C.c_double)),
+                ("values", C.POINTER(C.c_double)), ("antibodyconcens", C.POINTER(C.c_double))]
 
 
 class SprB200Error(RuntimeError):
@@ -113,6 +118,10 @@ def load():
     L.sprb200_build_indices.argtypes = [vp, P(SprGrid), P(SprSim), P(SprRun), P(i64), i64, P(dbl), P(i32), P(u64)]
     L.sprb200_scatter_rows_device.restype = C.c_int
     L.sprb200_scatter_rows_device.argtypes = [vp, vp, P(i64), i64, i32, i64, vp]
+    L.sprb200_surrogate_load.restype = C.c_int
+    L.sprb200_surrogate_load.argtypes = [vp, P(SprGrid), i32, dbl, dbl, vp, i32]
+    L.sprb200_fit_loss.restype = C.c_int
+    L.sprb200_fit_loss.argtypes = [vp, P(SprAligned), P(dbl), i64, P(dbl)]
     if L.sprb200_abi_version() != ABI_VERSION:
         raise ImportError("libsprb200.so ABI version mismatch")
     _lib = L
@@ -284,6 +293,32 @@ class Engine:
         idx = np.ascontiguousarray(idx, dtype=np.int64)
         self._check(self.lib.sprb200_scatter_rows_device(self.h, C.c_void_p(d_rows), _ptr(idx, C.c_int64), len(idx),
                                                          T, P, C.c_void_p(d_table)))
+
+    def surrogate_load(self, grid, tsave, table, on_device=False):
+        """keeps a FirstMoment table ([T][P] C-order == (n1,n2,n3,n4,T) column-major) resident on the GPU;
+        `table` is a numpy array, or a raw device address when on_device"""
+        tsave = np.asarray(tsave, dtype=np.float64)
+        if on_device:
+            ptr = C.c_void_p(int(table))
+            keep = None
+        else:
+            keep = np.ascontiguousarray(table, dtype=np.float64)
+            ptr = C.c_void_p(keep.ctypes.data)
+        self._check(self.lib.sprb200_surrogate_load(self.h, C.byref(grid), len(tsave), float(tsave[0]), float(tsave[-1]),
+                                                    ptr, 1 if on_device else 0))
+
+    def fit_loss(self, times, values, antibodyconcens, optpars):
+        """surrogate_sprdata_error for a whole population: optpars [npop][5] -> loss [npop]"""
+        npts = np.array([len(t) for t in times], dtype=np.int32)
+        tt = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.float64) for t in times]))
+        vv = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in values]))
+        abc = np.ascontiguousarray(antibodyconcens, dtype=np.float64)
+        assert len(tt) == len(vv) and len(abc) == len(npts)
+        op = np.ascontiguousarray(optpars, dtype=np.float64).reshape(-1, 5)
+        loss = np.zeros(len(op))
+        al = SprAligned(len(npts), _ptr(npts, C.c_int32), _ptr(tt, C.c_double), _ptr(vv, C.c_double), _ptr(abc, C.c_double))
+        self._check(self.lib.sprb200_fit_loss(self.h, C.byref(al), _ptr(op, C.c_double), len(op), _ptr(loss, C.c_double)))
+        return loss
 
     def scatter_table_device(self, d_rows, idxstart, stride, count, T, P, d_table):
         self._check(self.lib.sprb200_scatter_table_device(self.h, C.c_void_p(d_rows), idxstart, stride, count, T, P,

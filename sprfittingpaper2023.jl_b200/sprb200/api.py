@@ -15,6 +15,11 @@ Same names, argument meaning and error behaviour as the Julia package (paths und
   save_surrogate_metadata, save_surrogate,
   save_surrogate_slice, build_surrogate_serial,
   build_surrogate_slice, merge_surrogate_slices src/surrogate.jl:9-332
+  AlignedData, get_aligned_data                src/spr_data.jl:9-62
+  surrogate_sprdata_error, checkranges,
+  rescale_logkon_max, fit_spr_data,
+  optpars_to_physpars,
+  update_pars_and_run_spr_sim, fitted_curves   src/fitting.jl:36-241, 264-278
 
 Everything that simulates runs on the GPU through libsprb200.so; there is no CPU path here.
 The reference writes JLD (HDF5) files; neither Julia nor HDF5 exist in this image, so the Python
@@ -501,3 +506,183 @@ class Surrogate:
             if wt != 0.0:
                 acc += wt * self.table[tuple(idx)]
         return acc
+
+
+# ------------------------------------------------------------------ spr_data.jl / fitting.jl: the consumer of the table
+class AlignedData:
+    """spr_data.jl:9-18: times[i], refdata[i] for antibodyconcens[i] (uM); antigenconcen in uM."""
+
+    def __init__(self, times, refdata, antibodyconcens, antigenconcen):
+        self.times = [np.asarray(t, dtype=np.float64) for t in times]
+        self.refdata = [np.asarray(r, dtype=np.float64) for r in refdata]
+        self.antibodyconcens = np.asarray(antibodyconcens, dtype=np.float64)
+        self.antigenconcen = float(antigenconcen)
+        for t, r in zip(self.times, self.refdata):
+            if len(t) != len(r):
+                raise ValueError("Found a column of SPR data times with a different length than the assoicated "
+                                 "column of SPR curve data.")
+
+
+def get_aligned_data(fname, antigenconcen=None):
+    """spr_data.jl:31-62: CSV with column pairs (time, response) per antibody concentration; the header of
+    every response column starts with the concentration; missing cells are skipped; the antigen
+    concentration is parsed from a file name of the form "text-AGCCONCEN_aligned.csv" unless given."""
+    if antigenconcen is None:
+        antigenconcen = float(os.path.basename(fname).split("-")[-1].split("_")[-2])
+    with open(fname) as f:
+        lines = [ln.rstrip("\n") for ln in f if ln.strip()]
+    headers = [h.strip() for h in lines[0].split(",")]
+    nabcs = len(headers) // 2
+    antibodyconcens = [float(headers[k].split("_")[0]) for k in range(1, 2 * nabcs, 2)]
+    cols = [[] for _ in headers]
+    for ln in lines[1:]:
+        for k, cell in enumerate(ln.split(",")[:len(headers)]):
+            cell = cell.strip()
+            if cell and cell.lower() not in ("missing", "nan", "na"):
+                cols[k].append(float(cell))
+    return AlignedData([cols[2 * k] for k in range(nabcs)], [cols[2 * k + 1] for k in range(nabcs)],
+                       antibodyconcens, antigenconcen)
+
+
+def _surrogate_grid(surrogate):
+    sp = surrogate.surpars
+    return _lib.make_grid(sp.logkon_range, sp.logkoff_range, sp.logkonb_range, sp.reach_range,
+                          tuple(surrogate.surrogate_size[:4]))
+
+
+def _resident(surrogate, device=0):
+    """uploads the table of `surrogate` to the engine of `device` once"""
+    eng = get_engine(device)
+    if getattr(eng, "_resident_surrogate", None) is not surrogate:
+        T = surrogate.table.shape[4]
+        flat = np.ascontiguousarray(surrogate.table.reshape(-1, order="F").reshape(T, -1))
+        eng.surrogate_load(_surrogate_grid(surrogate), surrogate.simpars.tsave, flat)
+        eng._resident_surrogate = surrogate
+    return eng
+
+
+def surrogate_sprdata_error(optpars, surrogate, aligneddat, device=0):
+    """fitting.jl:38-91 on the GPU.  optpars = [logkon, logkoff, logkonb, reach, logCP] or a whole population
+    [npop][5] (one loss per row).  Outside the table the loss is +Inf (the reference throws BoundsError)."""
+    eng = _resident(surrogate, device)
+    op = np.asarray(optpars, dtype=np.float64)
+    loss = eng.fit_loss(aligneddat.times, aligneddat.refdata, aligneddat.antibodyconcens, op.reshape(-1, 5))
+    return float(loss[0]) if op.ndim == 1 else loss
+
+
+def checkranges(optranges, sr):
+    """fitting.jl:93-101"""
+    def inside(rsur, ropt):
+        return rsur[0] <= ropt[0] <= ropt[1] <= rsur[1]
+    for name, rs, ro in (("logkon", sr.logkon_range, optranges[0]), ("logkoff", sr.logkoff_range, optranges[1]),
+                         ("logkonb", sr.logkonb_range, optranges[2]), ("reach", sr.reach_range, optranges[3])):
+        if not inside(rs, ro):
+            raise ValueError("Optimizer %s_range not a subset of surrogate %s_optrange" % (name, name))
+
+
+def rescale_logkon_max(logkon, sur_logkon, abcs):
+    """fitting.jl:103-114: keeps logkon + log10(max(abcs)/abcs[1]) inside the surrogate"""
+    lkshift = math.log10(max(abcs) / abcs[0])
+    res = (logkon[0], logkon[1])
+    if logkon[1] + lkshift > sur_logkon[1]:
+        res = (logkon[0], sur_logkon[1] - lkshift)
+        if not res[0] <= res[1]:
+            raise ValueError("After the range given by logkon is smaller than needed to handle the provided changes "
+                             "in antibody concentration during fitting.")
+    return res
+
+
+class Optimiser:
+    """fitting.jl:1-20 carries an Optimization.jl method (BlackBoxOptim's xNES by default, :26-37).  Neither
+    package exists here; the stand-in is differential evolution (rand/1/bin with per-generation dither, the
+    family BlackBoxOptim defaults to) that evaluates each generation as ONE batched GPU loss call."""
+
+    def __init__(self, popsize=64, maxiters=400, F=(0.5, 1.0), CR=0.9, tol=1e-10, seed=None):
+        self.popsize, self.maxiters, self.F, self.CR, self.tol, self.seed = popsize, maxiters, F, CR, tol, seed
+
+
+class OptSolution:
+    def __init__(self, u, minimum, iters, evals):
+        self.u, self.minimum, self.iters, self.evals = u, minimum, iters, evals
+
+
+def fit_spr_data(surrogate, aligneddat, searchrange, optimiser=None, u0=None, device=0):
+    """fitting.jl:139-177.  searchrange = [logkon, logkoff, logkonb, reach, logCP] (lo, hi) pairs, or just
+    [logCP_range] to search the whole surrogate.  Returns (solution, [kon, koff, konb, reach, CP])."""
+    sp = surrogate.surpars
+    if len(searchrange) == 1:
+        sr = [tuple(sp.logkon_range), tuple(sp.logkoff_range), tuple(sp.logkonb_range), tuple(sp.reach_range),
+              tuple(searchrange[0])]
+    else:
+        sr = [tuple(r) for r in searchrange]
+    checkranges(sr, sp)
+    sr[0] = rescale_logkon_max(sr[0], sp.logkon_range, list(aligneddat.antibodyconcens))
+    lb = np.array([r[0] for r in sr], dtype=np.float64)
+    ub = np.array([r[1] for r in sr], dtype=np.float64)
+    opt = Optimiser() if optimiser is None else optimiser
+    rng = np.random.default_rng(_next_seed() if opt.seed is None else opt.seed)
+    NP = int(opt.popsize)
+    pop = lb + (ub - lb) * rng.random((NP, 5))
+    if u0 is not None:
+        pop[0] = np.clip(np.asarray(u0, dtype=np.float64), lb, ub)
+    cost = surrogate_sprdata_error(pop, surrogate, aligneddat, device)
+    evals, it = NP, 0
+    for it in range(1, int(opt.maxiters) + 1):
+        F = opt.F[0] + (opt.F[1] - opt.F[0]) * rng.random() if isinstance(opt.F, (tuple, list)) else opt.F
+        idx = np.array([rng.choice(NP - 1, size=3, replace=False) for _ in range(NP)])
+        idx += (idx >= np.arange(NP)[:, None])                       # three distinct members other than i
+        mutant = pop[idx[:, 0]] + F * (pop[idx[:, 1]] - pop[idx[:, 2]])
+        cross = rng.random((NP, 5)) < opt.CR
+        cross[np.arange(NP), rng.integers(0, 5, NP)] = True
+        trial = np.where(cross, mutant, pop)
+        # reflect at the bounds (stays inside the surrogate, like BlackBoxOptim's search space)
+        trial = np.where(trial < lb, np.minimum(2 * lb - trial, ub), trial)
+        trial = np.where(trial > ub, np.maximum(2 * ub - trial, lb), trial)
+        tcost = surrogate_sprdata_error(trial, surrogate, aligneddat, device)
+        evals += NP
+        better = tcost <= cost
+        pop[better], cost[better] = trial[better], tcost[better]
+        if np.isfinite(cost).all() and cost.max() - cost.min() <= opt.tol * max(abs(cost.min()), 1e-300):
+            break
+    k = int(np.argmin(cost))
+    sol = OptSolution(pop[k].copy(), float(cost[k]), it, evals)
+    return sol, optpars_to_physpars(sol.u, aligneddat, surrogate)
+
+
+def optpars_to_physpars(optpars, *args):
+    """fitting.jl:198-211: (optpars, antibodyconcen, antigenconcen, surrogate_antigenconcen) or
+    (optpars, aligned_data, surrogate): physical reach = internal reach * cbrt(agc_internal / agc_experiment)."""
+    if len(args) == 2:
+        ad, sur = args
+        abc, agc, sagc = ad.antibodyconcens[0], ad.antigenconcen, sur.surpars.antigenconcen
+    else:
+        abc, agc, sagc = args
+    return [10.0 ** optpars[0] / abc, 10.0 ** optpars[1], 10.0 ** optpars[2],
+            optpars[3] * (sagc / agc) ** (1.0 / 3.0), 10.0 ** optpars[4]]
+
+
+def update_pars_and_run_spr_sim(outputter, logpars, simpars, seed=None, device=0):
+    """fitting.jl:227-241: forward simulation at the optimiser's parameters (antibody concentration folded
+    into kon, CP applied by the outputter)."""
+    antigenconcen = inv_cubic_nm_to_muM(getantigenconcen(simpars))
+    biopars = biopars_from_fitting_vec(logpars, antigenconcen=antigenconcen, antibodyconcen=1.0)
+    outputter()
+    run_spr_sim(outputter, biopars, simpars, seed=seed, device=device)
+
+
+def fitted_curves(optsol, aligneddat, simpars, seed=None, device=0):
+    """the simulation half of visualisefit / savefit (fitting.jl:264-278, 331-345): for every antibody
+    concentration, mean bound response of simpars.nsims forward simulations at the fitted parameters, saved at
+    the data times.  Returns a list of arrays aligned with aligneddat.times (plotting/XLSX are out of scope)."""
+    params = list(optsol.u if hasattr(optsol, "u") else optsol)
+    out = []
+    abcref = aligneddat.antibodyconcens[0]
+    for i, abc in enumerate(aligneddat.antibodyconcens):
+        ps = list(params)
+        ps[0] = params[0] + math.log10(abc / abcref)
+        o = TotalBoundOutputter(len(aligneddat.times[i]))
+        simpars.tsave = np.asarray(aligneddat.times[i], dtype=np.float64)
+        simpars.tstop = float(aligneddat.times[i][-1])
+        update_pars_and_run_spr_sim(o, ps, simpars, seed=None if seed is None else seed + i, device=device)
+        out.append(means(o))
+    return out

@@ -1,0 +1,106 @@
+"""CPU: the fitting-side oracle (oracle/fit_oracle.py: surrogate lookup + l2 loss of fitting.jl:38-91) against
+closed forms, the aligned-data CSV reader (spr_data.jl:31-62) and the parameter conversions against the
+reference's recorded best fit (tests/golden/fit_curves_golden.json)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def affine_table(size, ranges, tsave, coef):
+    """table that is multilinear in the axis values (so multilinear interpolation is exact)"""
+    ax = [np.linspace(r[0], r[1], n) for r, n in zip(ranges, size[:4])] + [np.asarray(tsave)]
+    g = np.meshgrid(*ax, indexing="ij")
+    return coef[0] + coef[1] * g[0] + coef[2] * g[1] * g[2] + coef[3] * g[3] + coef[4] * g[4] * g[0]
+
+
+def test_interpolant_is_exact_on_multilinear_tables_and_loss_matches_closed_form():
+    from oracle import fit_oracle as F
+    size = (4, 3, 5, 3, 11)
+    ranges = [(-3.0, 1.0), (-2.0, 0.0), (-1.0, 1.0), (5.0, 25.0)]
+    tsave = np.linspace(0.0, 50.0, 11)
+    coef = (0.3, 0.02, 0.01, 0.004, 0.0007)
+    tab = affine_table(size, ranges, tsave, coef)
+    f = lambda x1, x2, x3, x4, t: coef[0] + coef[1] * x1 + coef[2] * x2 * x3 + coef[3] * x4 + coef[4] * t * x1
+    rng = np.random.default_rng(3)
+    times = [np.sort(rng.uniform(0.0, 50.0, 17)), np.sort(rng.uniform(0.0, 50.0, 9))]
+    abcs = [25.0, 100.0]
+    refdata = [rng.normal(1.0, 0.2, 17), rng.normal(2.0, 0.2, 9)]
+    for _ in range(20):
+        op = [rng.uniform(-3.0, 1.0 - math.log10(4.0)), rng.uniform(-2, 0), rng.uniform(-1, 1), rng.uniform(5, 25),
+              rng.uniform(0, 1)]
+        want = 0.0
+        for j, abc in enumerate(abcs):
+            x1 = op[0] + math.log10(abc / abcs[0])
+            for t, d in zip(times[j], refdata[j]):
+                want += (10.0 ** op[4] * f(x1, op[1], op[2], op[3], t) - d) ** 2
+        got = F.surrogate_sprdata_error(op, tab, ranges, tsave, times, refdata, abcs)
+        assert got == pytest.approx(want, rel=1e-12)
+    # nodes reproduce the table, the last node of every axis is inside, one step beyond is a BoundsError
+    assert F.itp(tab, (4, 3, 5, 3, 11)) == pytest.approx(tab[3, 2, 4, 2, 10], rel=1e-15)
+    assert F.itp(tab, (1, 1, 1, 1, 1)) == tab[0, 0, 0, 0, 0]
+    with pytest.raises(IndexError):
+        F.itp(tab, (4.0001, 1, 1, 1, 1))
+    with pytest.raises(IndexError):
+        F.itp(tab, (1, 1, 1, 1, 0.999))
+
+
+def test_oracle_agrees_with_the_package_interpolant():
+    """api.Surrogate.itp (the host mirror of surrogate.jl:66-70) and the oracle are independent restatements"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "sprfittingpaper2023.jl_b200"))
+    from oracle import fit_oracle as F
+    from sprb200 import api
+    rng = np.random.default_rng(11)
+    tab = rng.random((3, 4, 2, 5, 6))
+    sur = api.Surrogate(tab)
+    for _ in range(50):
+        q = [rng.uniform(1, n) for n in tab.shape]
+        assert sur.itp(*q) == pytest.approx(F.itp(tab, q), rel=1e-13)
+
+
+def test_get_aligned_data_reads_the_reference_csv_layout(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "sprfittingpaper2023.jl_b200"))
+    from sprb200 import api
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "fit_curves_golden.json")))
+    t = gold["times"]
+    d0, d1 = gold["data"]
+    # the reference's file: header "time (s), 25.000000,time (s), 100.000000", one row per time, ragged tail allowed
+    fn = tmp_path / "Data_FC4_test_RBD-13.8_aligned.csv"
+    with open(fn, "w") as f:
+        f.write("time (s), 25.000000,time (s), 100.000000\n")
+        for k in range(len(t)):
+            if k < len(t) - 3:
+                f.write("%.18e,%.18e,%.18e,%.18e\n" % (t[k], d0[k], t[k], d1[k]))
+            else:
+                f.write("%.18e,%.18e,,\n" % (t[k], d0[k]))          # missing cells in the second curve
+    ad = api.get_aligned_data(str(fn))
+    assert ad.antigenconcen == 13.8 and list(ad.antibodyconcens) == [25.0, 100.0]
+    assert np.array_equal(ad.times[0], np.array(t)) and np.array_equal(ad.refdata[0], np.array(d0))
+    assert len(ad.times[1]) == len(t) - 3 and np.array_equal(ad.refdata[1], np.array(d1[:-3]))
+    assert api.get_aligned_data(str(fn), 99.0).antigenconcen == 99.0
+
+
+def test_parameter_conversions_match_the_recorded_fit():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "sprfittingpaper2023.jl_b200"))
+    from sprb200 import api
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "fit_curves_golden.json")))
+    ip, pp = gold["internal_params"], gold["physical_params"]
+    op = [ip["logkon"], ip["logkoff"], ip["logkonb"], ip["reach"], ip["logCP"]]
+    phys = api.optpars_to_physpars(op, gold["antibody_nM"][0], 13.8, gold["antigenconcen_internal_uM"])
+    for got, name in zip(phys, ("kon", "koff", "konb", "reach", "CP")):
+        assert got == pytest.approx(pp[name], rel=1e-12), name
+    sp = api.SurrogateParams((-5.0, 2.0), (-4.0, 0.0), (-3.0, 1.5), (2.0, 35.0))
+    api.checkranges([(-4, 1), (-3, 0), (-3, 1), (2, 35), (1, 3)], sp)
+    with pytest.raises(ValueError):
+        api.checkranges([(-6, 1), (-3, 0), (-3, 1), (2, 35), (1, 3)], sp)
+    # a 4x concentration range needs log10(4) of head room at the top of the logkon axis (fitting.jl:103-114)
+    lo, hi = api.rescale_logkon_max((-5.0, 2.0), sp.logkon_range, [25.0, 100.0])
+    assert lo == -5.0 and hi == pytest.approx(2.0 - math.log10(4.0))
+    assert api.rescale_logkon_max((-5.0, 1.0), sp.logkon_range, [25.0, 100.0]) == (-5.0, 1.0)

@@ -1,0 +1,68 @@
+"""-m gpu: the consumer side of the table.  The batched loss kernel (sprb200_fit_loss) against the CPU
+restatement of fitting.jl:38-91 (oracle/fit_oracle.py) to 1e-12, and a small end-to-end fit: surrogate built
+on the GPU -> fit of the reference's aligned data set -> parameters near the reference's documented best fit."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_fit_loss_kernel_matches_oracle(engine):
+    from oracle import fit_oracle as F
+    from sprb200 import _lib
+    rng = np.random.default_rng(5)
+    size = (4, 3, 5, 3, 11)
+    ranges = [(-3.0, 1.0), (-2.0, 0.0), (-1.0, 1.0), (5.0, 25.0)]
+    tsave = np.linspace(0.0, 50.0, 11)
+    tab = rng.random(size)
+    grid = _lib.make_grid(*ranges, size[:4])
+    flat = np.ascontiguousarray(tab.reshape(-1, order="F").reshape(size[4], -1))     # [T][P]
+    engine.surrogate_load(grid, tsave, flat)
+    times = [np.sort(rng.uniform(0.0, 50.0, 37)), np.sort(rng.uniform(0.0, 50.0, 23)), np.array([0.0, 50.0])]
+    refdata = [rng.normal(1.0, 0.3, 37), rng.normal(2.0, 0.3, 23), np.array([0.5, 0.7])]
+    abcs = [25.0, 100.0, 50.0]
+    shift = math.log10(4.0)
+    pop = np.column_stack([rng.uniform(-3.0, 1.0 - shift, 64), rng.uniform(-2, 0, 64), rng.uniform(-1, 1, 64),
+                           rng.uniform(5, 25, 64), rng.uniform(-1, 2, 64)])
+    pop[0] = [-3.0, -2.0, -1.0, 5.0, 0.0]                       # lower corner of the table
+    pop[1] = [1.0 - shift, 0.0, 1.0, 25.0, 1.0]                 # upper corner (q == n on every axis)
+    loss = engine.fit_loss(times, refdata, abcs, pop)
+    for k in range(len(pop)):
+        want = F.surrogate_sprdata_error(pop[k], tab, ranges, tsave, times, refdata, abcs)
+        assert loss[k] == pytest.approx(want, rel=1e-12), k
+    # outside the table: +Inf (the reference throws BoundsError)
+    bad = np.array([[1.0 - shift + 1e-6, -1, 0, 10, 0], [-3.1, -1, 0, 10, 0], [0, 0.1, 0, 10, 0], [0, -1, 0, 25.5, 0]])
+    assert np.all(np.isinf(engine.fit_loss(times, refdata, abcs, bad)))
+    assert np.isinf(engine.fit_loss([np.array([51.0])], [np.array([1.0])], [25.0], pop[:1])[0])
+
+
+def test_end_to_end_fit_recovers_the_documented_parameters(engine):
+    """config 5 in miniature: a coarse surrogate around the documented optimum (13 s of the reference's CPU
+    time per grid point there; a fraction of a second for the whole grid here), then the fit"""
+    from sprb200 import api
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "fit_curves_golden.json")))
+    times = np.array(gold["times"])
+    ad = api.AlignedData([times, times], gold["data"], gold["antibody_nM"], 13.8)
+    surpars = api.SurrogateParams((-3.6, -1.8), (-2.0, -0.8), (-0.9, 0.6), (9.0, 21.0))
+    size = (10, 9, 7, 9, 151)
+    simpars = api.SimParams(tstop=600.0, tstop_AtoB=150.0, tsave=np.linspace(0.0, 600.0, 151), nsims=60)
+    table = api.build_surrogate_serial(size, surpars, simpars, terminator=api.SimNumberTerminator(), seed=20231)
+    sur = api.Surrogate(table, surpars=surpars, simpars=simpars, surrogate_size=size)
+    ip = gold["internal_params"]
+    pub = [ip["logkon"], ip["logkoff"], ip["logkonb"], ip["reach"], ip["logCP"]]
+    loss_pub = api.surrogate_sprdata_error(pub, sur, ad)
+    # the reference's own (finer, 100+ replicate) surrogate gives 78.99 at these parameters
+    assert 60.0 < loss_pub < 130.0, loss_pub
+    sol, phys = api.fit_spr_data(sur, ad, [(1.5, 2.7)], optimiser=api.Optimiser(popsize=48, maxiters=300, seed=1))
+    assert sol.minimum <= loss_pub + 1e-9
+    pp = gold["physical_params"]
+    # kon, koff and CP are well determined by the data; konb and reach trade off against each other
+    assert phys[0] == pytest.approx(pp["kon"], rel=0.25)
+    assert phys[1] == pytest.approx(pp["koff"], rel=0.25)
+    assert phys[4] == pytest.approx(pp["CP"], rel=0.15)
+    assert 0.3 < phys[2] / pp["konb"] < 3.0 and 0.7 < phys[3] / pp["reach"] < 1.4
