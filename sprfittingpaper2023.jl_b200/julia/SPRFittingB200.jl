@@ -228,6 +228,53 @@ function build_surrogate_slice(surmetadata::Dict, idxstart, idxend; terminator=V
     out
 end
 
+# ---------------------------------------------------------------------------------------------
+# The consumer of the table: surrogate_sprdata_error (src/fitting.jl:38-91) for a whole population.
+struct SprAligned
+    nconc::Int32; npts::Ptr{Int32}; times::Ptr{Cdouble}; values::Ptr{Cdouble}; antibodyconcens::Ptr{Cdouble}
+end
+
+"""
+    load_surrogate!(surrogate::Surrogate; device=0)
+
+Uploads `surrogate`'s FirstMoment table once (`sprb200_surrogate_load`); it stays resident on the GPU.
+Needs the raw table: pass the `Array{Float64,5}` the surrogate was built from.
+"""
+function load_surrogate!(table::Array{Float64,5}, surpars::SurrogateParams, simpars::SimParams; device=0)
+    h = handle(device)
+    sz = size(table)
+    g = SprGrid((surpars.logkon_range[1], surpars.logkoff_range[1], surpars.logkonb_range[1], surpars.reach_range[1]),
+                (surpars.logkon_range[2], surpars.logkoff_range[2], surpars.logkonb_range[2], surpars.reach_range[2]),
+                (Int32(sz[1]), Int32(sz[2]), Int32(sz[3]), Int32(sz[4])))
+    ts = simpars.tsave
+    GC.@preserve table check(h, ccall((:sprb200_surrogate_load, LIB), Cint,
+        (Ptr{Cvoid}, Ref{SprGrid}, Int32, Cdouble, Cdouble, Ptr{Cdouble}, Int32),
+        h, g, Int32(sz[5]), first(ts), last(ts), table, Int32(0)))
+    nothing
+end
+
+"""
+    surrogate_sprdata_errors(population::Matrix{Float64}, aligneddat::AlignedData; device=0)
+
+`surrogate_sprdata_error` for every column `[logkon, logkoff, logkonb, reach, logCP]` of `population` in one
+GPU call (after `load_surrogate!`): what a population-based optimiser (BlackBoxOptim's xNES/DE) evaluates per
+generation.  `+Inf` where the reference would throw a BoundsError.
+"""
+function surrogate_sprdata_errors(population::Matrix{Float64}, aligneddat::AlignedData; device=0)
+    size(population, 1) == 5 || error("population must be 5 x npop")
+    h = handle(device)
+    npts = Int32.(length.(aligneddat.times))
+    times = reduce(vcat, aligneddat.times); vals = reduce(vcat, aligneddat.refdata)
+    abcs = Vector{Float64}(aligneddat.antibodyconcens)
+    loss = Vector{Float64}(undef, size(population, 2))
+    GC.@preserve npts times vals abcs population loss begin
+        al = SprAligned(Int32(length(npts)), pointer(npts), pointer(times), pointer(vals), pointer(abcs))
+        check(h, ccall((:sprb200_fit_loss, LIB), Cint, (Ptr{Cvoid}, Ref{SprAligned}, Ptr{Cdouble}, Int64, Ptr{Cdouble}),
+                       h, al, population, size(population, 2), loss))
+    end
+    loss
+end
+
 """
     enable!()
 
