@@ -1,8 +1,8 @@
 """Paper-scale surrogate (examples/cluster_scripts/make_surrogate_metadata.jl ranges, size
 (42,40,30,30,601) = 1,512,000 points): the share of ONE rank of `world` ranks (block-cyclic over the linear
 index, block = 1680 points = one (konb, reach) pair), FIXED 100 replicates -- what each GPU of an 8-GPU
-build does.  Prints time, events, a checksum, and checks a few random points of the share against the CPU
-oracle of the reference algorithm (two-sample z test per save slot).
+build does.  Prints time, events and a checksum; tests/tools/c3_sample_parity.py checks random points of the grid against
+the CPU oracle of the reference algorithm.
 usage: c3_share.py [world=8] [rank=0] [nrep=100] [variance]"""
 import hashlib, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -37,28 +37,3 @@ print("n_used mean %.1f min %d max %d; events/trajectory mean %.0f max-point %.0
       (nu.mean(), nu.min(), nu.max(), nev.sum() / max(st["trajectories"], 1), (nev / np.maximum(nu, 1)).max(),
        hashlib.sha256(rows.tobytes()).hexdigest()[:16]))
 assert np.all(rows[:, 0] == 0.0) and np.all(rows >= 0.0) and np.all(rows <= 1.0)
-# ---- parity of a few random points of the share against the CPU oracle of the reference algorithm
-from oracle import ref_oracle as R
-R.build()
-import ctypes as C
-rng = np.random.default_rng(5)
-pick = rng.choice(len(idx), size=6, replace=False)
-lib = _lib.load(); p = _lib.SprPoint()
-rs = R.make_sim(N=1000, DIM=3, tstop=600.0, tstop_AtoB=150.0, tsave=tsave, L=L, nsims=100)
-worst = 0.0
-for k in pick:
-    lib.sprb200_grid_point(C.byref(grid), int(idx[k]), C.byref(p))
-    pt = [p.kon_eff, p.koff, p.konb, p.reach]
-    out = eng.simulate(sim, [pt], _lib.make_run(nsims=400, seed=99), want=("sum", "sumsq", "n_used"))
-    n = int(out["n_used"][0])
-    gm = out["sum"][0] / n / 1000.0
-    gv = (out["sumsq"][0] - out["sum"][0].astype(float) ** 2 / n) / (n - 1) / 1000.0 ** 2
-    ro = R.run(*pt, rs, seed=int(idx[k]) % 100000 + 1)
-    se = np.sqrt(gv / n + ro["var"] / ro["n"])
-    ok = se > 0
-    z = np.abs((gm - ro["mean"])[ok] / se[ok]).max() if ok.any() else 0.0
-    tz = np.abs(rows[k] - gm).max()
-    worst = max(worst, z)
-    print("  idx %8d  kon' %.3g koff %.3g konb %.3g reach %.2f : max|z| vs oracle %.2f (table row vs 400-replicate rerun max diff %.4f)" %
-          (idx[k], *pt, z, tz), flush=True)
-print("worst max|z| over 6 points x 600 slots: %.2f" % worst)
