@@ -119,7 +119,7 @@ CASES = {
 
 
 # (GPU seed, oracle seed) per case: fixed constants taken from the seed grid evaluated on the CPU with the
-# mirror (scripts/parity_null_check.py; the GPU equals the mirror bit for bit).  Under the null -- oracle
+# mirror (tests/tools/parity_null_check.py; the GPU equals the mirror bit for bit).  Under the null -- oracle
 # vs mirror, no systematic sign -- max|z| over the ~600 autocorrelated save slots exceeds 3 for about one
 # seed pair in five (profiles/r1_parity_null_seedgrid_*.txt), so the seeds must be pinned for the 3-SE
 # criterion of the north star to be a deterministic test.
