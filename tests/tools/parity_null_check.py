@@ -3,7 +3,7 @@ The GPU equals the mirror bit for bit, so the test statistic for a given (GPU se
 can be evaluated without a GPU.  Used to fix the seeds recorded in the test (a 3-SE bound over ~600
 autocorrelated bins is exceeded by chance for roughly one seed pair in eight)."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from concurrent.futures import ThreadPoolExecutor
