@@ -9,9 +9,10 @@ Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): ranges of
 log10 konb -3..1.5, reach 2..35 nm, tstop 600, tstop_AtoB 150, tsave = range(0,600,601)), default
 geometry (N = 1000, L = 236.686 nm, DIM 3, resampled positions), FIXED 100 replicates per point,
 size (10,10,10,10*N_gpus): 10^4 points = 10^6 trajectories PER GPU (weak scaling).  The linear
-index range is dealt to the ranks block-cyclically (one block = one reach value = 1000 points), each
-rank simulates its own points with no data-path collective, and one NCCL all-gather assembles the
-table, which is permuted on the device into the "FirstMoment" layout fitting.jl consumes.
+grid points are dealt to the ranks in snake order of the library's a-priori cost estimate (every rank gets
+the same cost mix), each rank simulates its own points with no data-path collective, and one NCCL
+all-gather assembles the table, which is permuted on the device into the "FirstMoment" layout
+fitting.jl consumes.
 
 A step = one complete build.  `value` = SSA events/s with inputs resident (device API, output stays in
 HBM); `e2e` = the same through the host-buffer C-ABI call (H2D of the step's inputs, D2H of the
@@ -55,7 +56,7 @@ def config(world):
         "points_per_gpu": NK[0] * NK[1] * NK[2] * NREACH_PER_GPU,
         "replicates": NREP,
         "trajectories_per_gpu": NK[0] * NK[1] * NK[2] * NREACH_PER_GPU * NREP,
-        "sharding": "block-cyclic over the linear parameter index (block = 1000 points = one reach value); "
+        "sharding": "grid points dealt to ranks in snake order of the a-priori cost estimate (equal cost mix per rank); "
                     "NCCL all-gather of the mean-curve slabs only",
         "l2": "no flush needed: every step streams >1.2 GB of replicate curves per GPU (L2 is 126 MB) and all "
               "trajectory state lives in shared memory",
@@ -63,14 +64,23 @@ def config(world):
     }
 
 
+_deal_cache = {}
+
+
 def rank_indices(world, rank):
-    """1-based linear indices of this rank (block-cyclic, block = one reach value)."""
-    blk = NK[0] * NK[1] * NK[2]
-    nblocks = NREACH_PER_GPU * world
-    out = []
-    for b in range(rank, nblocks, world):
-        out.append(np.arange(b * blk + 1, (b + 1) * blk + 1, dtype=np.int64))
-    return np.concatenate(out)
+    """1-based linear indices of this rank.  Cost-balanced deal: the grid points, sorted by the library's
+    a-priori cost estimate, are handed to the ranks in snake order, so every rank simulates the same
+    mix of cheap and expensive points (a block-cyclic deal by reach value left the last rank 5 % more
+    work at 8 GPUs: profiles/r1_bench_c2_8gpu_blockcyclic.json)."""
+    if world not in _deal_cache:
+        from sprb200 import _lib
+        import sprb200
+        grid = _lib.make_grid(RANGES["logkon"], RANGES["logkoff"], RANGES["logkonb"], RANGES["reach"],
+                              NK + (NREACH_PER_GPU * world,))
+        sim = sprb200.SimSpec(NPART, DIM, _lib.domain_length(NPART, DIM), TSTOP, TOFF, np.linspace(0.0, TSTOP, NT))
+        cost = _lib.estimate_cost(sim, _lib.grid_points(grid))
+        _deal_cache[world] = [d + 1 for d in _lib.balanced_deal(cost, world)]
+    return _deal_cache[world][rank]
 
 
 def mean_degree(reach, L):
@@ -219,6 +229,9 @@ def main():
         return 2
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL writes its version banner to stdout (NCCL_DEBUG=VERSION on some boxes): keep stdout to the JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = sprb200.Engine(local_rank)
     L = _lib.domain_length(NPART, DIM)

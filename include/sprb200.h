@@ -140,6 +140,11 @@ int sprb200_last_kernel_ms(sprb200_handle h, double *table_ms, double *traj_ms);
  * SPRB200_ERR_TOO_LARGE when one trajectory does not fit. */
 int sprb200_traj_layout(int32_t N, int32_t wide_state, int32_t wide_offsets, int32_t out[4]);
 
+/* Rough relative cost (SSA events x neighbour work of one replicate) of each point: the ordering the library
+ * itself uses to start expensive points first.  Device-free; callers use it to deal points to ranks so
+ * that every GPU gets the same cost mix (bench.py).  sim->tsave may be NULL here. */
+int sprb200_estimate_cost(const SprSim *sim, const SprPoint *pts, int64_t npts, double *cost_out);
+
 /* ---- helpers --------------------------------------------------------------------------- */
 /* L = (N / agc)^(1/DIM), agc = 6.02214076e-7*antigenconcen if convert_units (parameters.jl:138-139) */
 double sprb200_domain_length(int32_t N, int32_t DIM, double antigenconcen, int32_t convert_units);

@@ -731,6 +731,16 @@ int sprb200_last_kernel_ms(sprb200_handle h, double *table_ms, double *traj_ms) 
     return SPRB200_OK;
 }
 
+int sprb200_estimate_cost(const SprSim *sim, const SprPoint *pts, int64_t npts, double *cost_out) {
+    if (!sim || !pts || !cost_out || npts < 0 || sim->N < 1 || (sim->DIM != 2 && sim->DIM != 3) || !(sim->L > 0.0))
+        return SPRB200_ERR_BAD_ARG;
+    for (int64_t k = 0; k < npts; ++k) {
+        const PointDev p{pts[k].kon_eff, pts[k].koff, pts[k].konb, pts[k].reach};
+        cost_out[k] = cost_estimate(p, sim->N, sim->DIM, sim->L, sim->tstop, sim->tstop_AtoB);
+    }
+    return SPRB200_OK;
+}
+
 int sprb200_traj_layout(int32_t N, int32_t wide_state, int32_t wide_offsets, int32_t out[4]) {
     if (!out || N < 1 || N > 65535) return SPRB200_ERR_BAD_ARG;
     TrajLayout lay;

@@ -16,7 +16,7 @@ OBS_TOTAL_BOUND, OBS_TOTAL_A = 0, 1
 
 EXPORTS = [
     "sprb200_abi_version", "sprb200_create", "sprb200_destroy", "sprb200_last_error", "sprb200_last_stats",
-    "sprb200_last_kernel_ms", "sprb200_traj_layout", "sprb200_surrogate_load", "sprb200_fit_loss",
+    "sprb200_last_kernel_ms", "sprb200_traj_layout", "sprb200_estimate_cost", "sprb200_surrogate_load", "sprb200_fit_loss",
     "sprb200_domain_length", "sprb200_grid_value", "sprb200_grid_point", "sprb200_simulate",
     "sprb200_simulate_raw", "sprb200_neighbor_table", "sprb200_build_slice", "sprb200_build_table",
     "sprb200_merge_slice", "sprb200_build_slice_device", "sprb200_scatter_table_device",
@@ -85,6 +85,8 @@ def load():
     L.sprb200_last_error.argtypes = [vp]
     L.sprb200_last_stats.restype = C.c_int
     L.sprb200_last_stats.argtypes = [vp, P(u64), P(u64), P(u64), P(dbl)]
+    L.sprb200_estimate_cost.restype = C.c_int
+    L.sprb200_estimate_cost.argtypes = [P(SprSim), P(SprPoint), i64, P(dbl)]
     L.sprb200_traj_layout.restype = C.c_int
     L.sprb200_traj_layout.argtypes = [i32, i32, i32, P(i32)]
     L.sprb200_last_kernel_ms.restype = C.c_int
@@ -130,6 +132,41 @@ def load():
 
 def _ptr(a, ct):
     return a.ctypes.data_as(C.POINTER(ct)) if a is not None else None
+
+
+def estimate_cost(sim, points):
+    """relative cost of one replicate of each point [npts][4] (kon', koff, konb, reach)"""
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 4)
+    out = np.zeros(len(pts))
+    rc = load().sprb200_estimate_cost(C.byref(sim.c), pts.ctypes.data_as(C.POINTER(SprPoint)), len(pts), _ptr(out, C.c_double))
+    if rc != OK:
+        raise SprB200Error(rc, "bad arguments to sprb200_estimate_cost")
+    return out
+
+
+def grid_points(grid, idx=None):
+    """parameter points [n][4] of 1-based linear grid indices (all of them by default)"""
+    L = load()
+    P = int(np.prod([grid.n[k] for k in range(4)]))
+    idx = np.arange(1, P + 1, dtype=np.int64) if idx is None else np.asarray(idx, dtype=np.int64)
+    out = np.zeros((len(idx), 4))
+    p = SprPoint()
+    for k, i in enumerate(idx):
+        if L.sprb200_grid_point(C.byref(grid), int(i), C.byref(p)) != OK:
+            raise SprB200Error(ERR_BAD_ARG, "index outside the grid")
+        out[k] = (p.kon_eff, p.koff, p.konb, p.reach)
+    return out
+
+
+def balanced_deal(costs, world):
+    """deals items to `world` ranks so that every rank gets the same cost mix: items sorted by cost
+    (descending, ties by index) are handed out in snake order 0..w-1, w-1..0, ...  Returns a list of
+    0-based index arrays (each sorted ascending)."""
+    order = np.lexsort((np.arange(len(costs)), -np.asarray(costs, dtype=np.float64)))
+    pos = np.arange(len(order))
+    lap, within = pos // world, pos % world
+    rank = np.where(lap % 2 == 0, within, world - 1 - within)
+    return [np.sort(order[rank == r]) for r in range(world)]
 
 
 def traj_layout(N, wide_state=False, wide_offsets=False):

@@ -110,3 +110,25 @@ def test_shared_memory_plan(built_lib):
     with pytest.raises(_lib.SprB200Error) as e:
         _lib.traj_layout(40000)
     assert e.value.code == _lib.ERR_TOO_LARGE
+
+
+def test_cost_balanced_deal(built_lib):
+    """the multi-GPU deal of bench.py: a partition of the grid, equal sizes, near-equal estimated cost per rank"""
+    import sprb200
+    from sprb200 import _lib
+    grid = _lib.make_grid((-3, 2), (-4, -1), (-3, 1.5), (2, 35), (10, 10, 10, 16))
+    pts = _lib.grid_points(grid)
+    assert pts.shape == (16000, 4) and pts[0, 3] == 2.0 and pts[-1, 3] == 35.0
+    sim = sprb200.SimSpec(1000, 3, _lib.domain_length(), 600.0, 150.0, np.linspace(0, 600, 601))
+    cost = _lib.estimate_cost(sim, pts)
+    assert np.all(cost > 0) and cost[-1] > cost[0]
+    for world in (1, 2, 3, 8):
+        deal = _lib.balanced_deal(cost, world)
+        allidx = np.concatenate(deal)
+        assert len(deal) == world and np.array_equal(np.sort(allidx), np.arange(16000))
+        sizes = [len(d) for d in deal]
+        assert max(sizes) - min(sizes) <= 1
+        sums = np.array([cost[d].sum() for d in deal])
+        assert sums.max() / sums.min() < 1.002
+    # deterministic (every rank computes the same deal)
+    assert all(np.array_equal(a, b) for a, b in zip(_lib.balanced_deal(cost, 8), _lib.balanced_deal(cost.copy(), 8)))
