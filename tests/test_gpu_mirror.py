@@ -46,6 +46,11 @@ CASES = [
     (0.05, 0.01, 0.3, 25.0, 600, 2, 100.0, 400.0),
     (0.02, 0.05, 0.5, 10.0, 1000, 3, float("inf"), 200.0),
     (0.5, 0.5, 5.0, 60.0, 200, 3, 20.0, 60.0),
+    # the wide instantiations of the trajectory kernel: degree > 127 (32-bit state words), more than 65,535
+    # table entries (32-bit offsets), and both
+    (0.3, 0.3, 0.05, 200.0, 200, 3, 10.0, 30.0),
+    (0.05, 0.1, 0.02, 60.5, 1000, 3, 20.0, 40.0),
+    (0.3, 0.3, 0.02, 300.0, 300, 3, 10.0, 30.0),
 ]
 
 
