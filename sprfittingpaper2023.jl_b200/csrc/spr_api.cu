@@ -19,7 +19,7 @@ using namespace spr;
 
 namespace {
 
-constexpr int NSTREAM = 4;
+constexpr int NSTREAM = 1;   // every launch of a handle is ordered on one non-default stream
 thread_local std::string g_create_error;
 
 struct DevBuf {
@@ -271,6 +271,9 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
         for (int64_t k = 0; k < npts; ++k) maxreach = std::max(maxreach, pts[k].reach);
         stage_cap = table_stage_cap(N, DIM, sim->L, maxreach);
         if (h->stage_cap_override > 0) stage_cap = std::min(stage_cap, std::max(1, h->stage_cap_override));
+        // at most 2 GB of staging: a denser table than the stride allows takes K2's second-pass path
+        const size_t rows_total = (size_t)k2_ctas * h->num_sms * (size_t)N;
+        stage_cap = (int)std::max<size_t>(8, std::min<size_t>((size_t)stage_cap, ((size_t)2 << 30) / (rows_total * sizeof(uint16_t))));
         CUDA_TRY(h, h->stage.ensure(sizeof(uint16_t) * (size_t)k2_ctas * h->num_sms * (size_t)N * (size_t)stage_cap));
     }
     {   // the narrowest trajectory layout must fit one warp's slice
