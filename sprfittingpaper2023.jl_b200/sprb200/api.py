@@ -686,3 +686,61 @@ def fitted_curves(optsol, aligneddat, simpars, seed=None, device=0):
         update_pars_and_run_spr_sim(o, ps, simpars, seed=None if seed is None else seed + i, device=device)
         out.append(means(o))
     return out
+
+
+# ------------------------------------------------------------------ hand-over to Julia without HDF5
+def _toml_value(v):
+    if isinstance(v, (list, tuple, np.ndarray)):
+        return "[" + ", ".join(_toml_value(x) for x in np.asarray(v).tolist()) + "]"
+    if isinstance(v, (bool, np.bool_)):
+        return "true" if v else "false"
+    if isinstance(v, (int, np.integer)):
+        return str(int(v))
+    v = float(v)
+    if math.isinf(v):
+        return "inf" if v > 0 else "-inf"
+    if math.isnan(v):
+        return "nan"
+    return repr(v)                                   # shortest round-trip decimal of the double
+
+
+def export_surrogate_raw(basename, source):
+    """Writes a surrogate in a container Julia reads with its standard library only: `basename.f64` = the
+    FirstMoment array as raw little-endian Float64 in Julia's column-major order, `basename.toml` = every
+    metadata key save_surrogate_metadata writes (surrogate.jl:112-123).  `source` is an .npz written by
+    save_surrogate / merge_surrogate_slices, or the dict load() returns.
+    sprfittingpaper2023.jl_b200/julia/raw_to_jld.jl turns the pair into the reference's .jld file with the
+    reference's own writer."""
+    data = load(source) if isinstance(source, str) else source
+    if "FirstMoment" not in data:
+        raise KeyError("FirstMoment")
+    table = np.asarray(data["FirstMoment"], dtype="<f8")
+    size = tuple(int(v) for v in data["surrogate_size"])
+    if table.shape != size:
+        raise ValueError("FirstMoment has shape %r, surrogate_size says %r" % (table.shape, size))
+    with open(basename + ".f64", "wb") as f:
+        f.write(np.asfortranarray(table).tobytes(order="F"))
+    keys = ["surrogate_size"] + list(_SURPAR_FIELDS) + ["N", "tstop", "tstop_AtoB", "tsave", "L", "DIM"]
+    if "seed" in data:
+        keys.append("seed")
+    with open(basename + ".toml", "w") as f:
+        f.write("# SPRFittingPaper2023 surrogate metadata (keys of save_surrogate_metadata); table in %s.f64,\n"
+                "# raw little-endian Float64, column-major (nkon, nkoff, nkonb, nreach, ntime)\n" % os.path.basename(basename))
+        for k in keys:
+            v = data[k]
+            if k in ("surrogate_size", "N", "DIM", "seed"):
+                v = np.asarray(v).astype(np.int64)
+            f.write("%s = %s\n" % (k, _toml_value(v.tolist() if isinstance(v, np.ndarray) and v.ndim == 0 else v)))
+    return basename + ".f64", basename + ".toml"
+
+
+def import_surrogate_raw(basename):
+    """inverse of export_surrogate_raw (round-trip check; needs tomllib, Python >= 3.11)"""
+    import tomllib
+    with open(basename + ".toml", "rb") as f:
+        meta = tomllib.load(f)
+    size = tuple(meta["surrogate_size"])
+    table = np.fromfile(basename + ".f64", dtype="<f8").reshape(size, order="F")
+    out = {k: np.asarray(v) for k, v in meta.items()}
+    out["FirstMoment"] = table
+    return out

@@ -109,3 +109,25 @@ def test_surrogate_files_and_interpolation(built_lib, tmp_path):
     with pytest.raises(FileExistsError):
         api.merge_surrogate_slices(meta, base, 2)
     api.merge_surrogate_slices(meta, base, 2, force=True)
+
+
+def test_raw_surrogate_handover_round_trips(built_lib, tmp_path):
+    """the HDF5-free hand-over to Julia (raw Float64 + TOML with the reference's metadata keys,
+    surrogate.jl:112-123): bytes are Julia's column-major array, every key survives, Inf included"""
+    from sprb200 import api
+    rng = np.random.default_rng(2)
+    size = (3, 2, 4, 2, 5)
+    surpars = api.SurrogateParams((-3.0, 2.0), (-4.0, -1.0), (-3.0, 1.5), (2.0, 35.0))
+    simpars = api.SimParams(tstop=4.0, tstop_AtoB=math.inf, tsave=np.linspace(0.0, 4.0, 5))
+    table = np.asfortranarray(rng.random(size))
+    meta = api._metadata_dict(size, surpars, simpars)
+    meta["FirstMoment"] = table
+    f64, toml = api.export_surrogate_raw(str(tmp_path / "sur"), meta)
+    raw = np.fromfile(f64, dtype="<f8")
+    assert raw.size == table.size and raw[1] == table[1, 0, 0, 0, 0] and raw[3] == table[0, 1, 0, 0, 0]   # kon fastest
+    back = api.import_surrogate_raw(str(tmp_path / "sur"))
+    assert np.array_equal(back["FirstMoment"], table)
+    for k in ("surrogate_size", "logkon_range", "logkoff_range", "logkonb_range", "reach_range", "antigenconcen",
+              "antibodyconcen", "CP", "N", "tstop", "tstop_AtoB", "tsave", "L", "DIM"):
+        assert np.array_equal(np.asarray(back[k], dtype=np.float64), np.asarray(meta[k], dtype=np.float64)), k
+    assert math.isinf(float(back["tstop_AtoB"]))
