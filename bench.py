@@ -358,8 +358,9 @@ def main():
         roofline_issue = {
             "bound": "issue", "achieved": ev_rate_kernel * I_ALG, "peak": issue_peak, "unit": "warp-inst/s",
             "frac": ev_rate_kernel * I_ALG / issue_peak,
-            "note": "flat-scan algorithmic warp-instructions per event I_alg = %.0f (SURVEY.md 8d); executed "
-                    "instructions per event are in profiles/ (ncu sm__inst_executed)" % I_ALG,
+            "note": "flat-scan algorithmic warp-instructions per event I_alg = %.0f (SURVEY.md 8d); executed: 202-224 "
+                    "warp-instructions per event, 56-65 %% of issue slots active (ncu sm__inst_executed / "
+                    "smsp__issue_active, profiles/r1_ncu_full_c2_class*.txt)" % I_ALG,
         }
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
