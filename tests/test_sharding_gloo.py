@@ -1,4 +1,4 @@
-"""CPU, world_size 2 over gloo: the multi-rank plumbing of the surrogate build (block-cyclic index
+"""CPU, world_size 2 over gloo: the multi-rank plumbing of the surrogate build (cost-balanced index
 deal, all-gather of the per-rank slabs, scatter into FirstMoment order) without GPUs.  The per-rank
 'simulation' is a deterministic function of the parameter index, exactly the property the GPU path has
 (RNG keyed by parameter index and replicate), so the gathered table must equal the single-rank one."""
@@ -38,11 +38,11 @@ def _worker(rank, world, port, tmp):
     P = len(idx_all)
     grid = _lib.make_grid((-3, 2), (-4, -1), (-3, 1.5), (2, 35), bench.NK + (bench.NREACH_PER_GPU * world,))
     table = np.zeros((T, P))
-    # host scatter = sprb200_merge_slice per contiguous block (same arithmetic as the device scatter)
-    blk = bench.NK[0] * bench.NK[1] * bench.NK[2]
-    for b in range(len(idx_all) // blk):
-        seg = idx_all[b * blk:(b + 1) * blk]
-        _lib.merge_slice(grid, T, all_rows[b * blk:(b + 1) * blk], int(seg[0]), int(seg[-1]), table)
+    # host scatter = sprb200_merge_slice per run of consecutive indices (same arithmetic as the device scatter
+    # sprb200_scatter_rows_device: table[s*P + idx-1] = rows[k*T + s])
+    cuts = np.flatnonzero(np.diff(idx_all) != 1) + 1
+    for a, b in zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [len(idx_all)]])):
+        _lib.merge_slice(grid, T, all_rows[a:b], int(idx_all[a]), int(idx_all[b - 1]), table)
     np.save(os.path.join(tmp, "table_%d.npy" % rank), table)
     dist.barrier()
     dist.destroy_process_group()
