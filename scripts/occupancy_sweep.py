@@ -1,4 +1,4 @@
-"""scratch: throughput vs resident trajectories per SM (SPRB200_MAX_BPS), and setup-only scaling."""
+"""scratch: throughput of the trajectory kernel vs resident trajectories per SM (SPRB200_MAX_WARPS)."""
 import os, sys, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if len(sys.argv) > 1 and sys.argv[1] == "child":
@@ -15,8 +15,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         eng.simulate(sim, [pt], r, want=("n_events",))
         st = eng.stats()
         ev = st["events"]; ms = st["device_ms"]
-        print("bps=%s %-28s traj %6d ev/traj %9.1f dev %8.2f ms %7.3f us/traj ev/s %.3e" %
-              (os.environ.get("SPRB200_MAX_BPS", "-"), name, nsims, ev / nsims, ms, ms * 1e3 / nsims, ev / (ms * 1e-3)), flush=True)
+        print("warps/SM=%s %-22s traj %6d ev/traj %9.1f K1 %8.2f ms  K1 ev/s %.3e" %
+              (os.environ.get("SPRB200_MAX_WARPS", "-"), name, nsims, ev / nsims, st["traj_ms"], ev / (st["traj_ms"] * 1e-3)), flush=True)
     mode = sys.argv[2]
     if mode == "setup":
         for n in (14800, 148000):
@@ -24,11 +24,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             run("setup only reach 16.67", [0.0, 0.1, 1.0, 16.67], n)
             run("setup only reach 35", [0.0, 0.1, 1.0, 35.0], n)
     else:
-        run("flips reach15", [1.0, 1.0, 0.0, 15.29], 14800, tstop=50.0, toff=50.0, T=51)
-        run("pingpong reach 15", [1.0, 0.1, 3.0, 15.29], 14800, tstop=200.0, toff=100.0, T=201)
-        run("pingpong reach 35", [1.0, 0.1, 3.0, 35.0], 14800, tstop=100.0, toff=50.0, T=101)
+        run("flips reach15", [1.0, 1.0, 0.0, 15.29], 29600, tstop=50.0, toff=50.0, T=51)
+        run("pingpong reach 15", [1.0, 0.1, 3.0, 15.29], 29600, tstop=200.0, toff=100.0, T=201)
+        run("pingpong reach 35", [1.0, 0.1, 3.0, 35.0], 29600, tstop=100.0, toff=50.0, T=101)
     sys.exit(0)
-subprocess.run([sys.executable, __file__, "child", "setup"])
-for bps in (4, 8, 12, 17):
-    env = dict(os.environ, SPRB200_MAX_BPS=str(bps))
+for bps in (5, 10, 15, 20, 25):
+    env = dict(os.environ, SPRB200_MAX_WARPS=str(bps))
     subprocess.run([sys.executable, __file__, "child", "events"], env=env)
