@@ -593,17 +593,99 @@ def rescale_logkon_max(logkon, sur_logkon, abcs):
 
 
 class Optimiser:
-    """fitting.jl:1-20 carries an Optimization.jl method (BlackBoxOptim's xNES by default, :26-37).  Neither
-    package exists here; the stand-in is differential evolution (rand/1/bin with per-generation dither, the
-    family BlackBoxOptim defaults to) that evaluates each generation as ONE batched GPU loss call."""
+    """fitting.jl:1-37 carries an Optimization.jl method; the reference's default for the bivalent model is
+    BlackBoxOptim's xNES (`BBO_xnes`, maxiters = 5000).  Neither package exists here, so both stand-ins are
+    written out: method = "de" (default here: differential evolution rand/1/bin with dither, population 64 --
+    it reaches the same minimum from every start on the reference's data set) and method = "xnes" (exponential
+    natural evolution strategy, Glasmachers et al. 2010, population 4 + floor(3 ln n) = 8 and the paper's
+    learning rates; this small-population implementation stops in a local minimum of the piecewise-multilinear
+    loss from most random starts on the reference's data set -- profiles/r1_config5_fit_demo.txt -- so, as
+    docs/src/fitting.md:55-66 does with the reference's xNES, run several fits and keep the best).  Either way
+    one generation = ONE batched GPU loss call."""
 
-    def __init__(self, popsize=64, maxiters=400, F=(0.5, 1.0), CR=0.9, tol=1e-10, seed=None):
-        self.popsize, self.maxiters, self.F, self.CR, self.tol, self.seed = popsize, maxiters, F, CR, tol, seed
+    def __init__(self, method="de", popsize=None, maxiters=None, F=(0.5, 1.0), CR=0.9, tol=1e-10, seed=None):
+        if method not in ("xnes", "de"):
+            raise ValueError("method must be 'xnes' or 'de'")
+        self.method = method
+        self.popsize = popsize if popsize is not None else (None if method == "xnes" else 64)
+        self.maxiters = maxiters if maxiters is not None else (5000 if method == "xnes" else 400)
+        self.F, self.CR, self.tol, self.seed = F, CR, tol, seed
 
 
 class OptSolution:
     def __init__(self, u, minimum, iters, evals):
         self.u, self.minimum, self.iters, self.evals = u, minimum, iters, evals
+
+
+def _reflect(x, lb, ub):
+    x = np.where(x < lb, np.minimum(2 * lb - x, ub), x)
+    return np.where(x > ub, np.maximum(2 * ub - x, lb), x)
+
+
+def minimise_de(f, lb, ub, rng, popsize=64, maxiters=400, F=(0.5, 1.0), CR=0.9, tol=1e-10, u0=None):
+    """differential evolution rand/1/bin; f maps a population [NP][n] to costs [NP]"""
+    n = len(lb)
+    NP = int(popsize)
+    pop = lb + (ub - lb) * rng.random((NP, n))
+    if u0 is not None:
+        pop[0] = np.clip(np.asarray(u0, dtype=np.float64), lb, ub)
+    cost = np.asarray(f(pop), dtype=np.float64)
+    evals, it = NP, 0
+    for it in range(1, int(maxiters) + 1):
+        Fk = F[0] + (F[1] - F[0]) * rng.random() if isinstance(F, (tuple, list)) else F
+        idx = np.array([rng.choice(NP - 1, size=3, replace=False) for _ in range(NP)])
+        idx += (idx >= np.arange(NP)[:, None])                       # three distinct members other than i
+        mutant = pop[idx[:, 0]] + Fk * (pop[idx[:, 1]] - pop[idx[:, 2]])
+        cross = rng.random((NP, n)) < CR
+        cross[np.arange(NP), rng.integers(0, n, NP)] = True
+        trial = _reflect(np.where(cross, mutant, pop), lb, ub)       # stays inside the search box
+        tcost = np.asarray(f(trial), dtype=np.float64)
+        evals += NP
+        better = tcost <= cost
+        pop[better], cost[better] = trial[better], tcost[better]
+        if np.isfinite(cost).all() and cost.max() - cost.min() <= tol * max(abs(cost.min()), 1e-300):
+            break
+    k = int(np.argmin(cost))
+    return OptSolution(pop[k].copy(), float(cost[k]), it, evals)
+
+
+def minimise_xnes(f, lb, ub, rng, popsize=None, maxiters=5000, tol=1e-10, u0=None):
+    """xNES in the unit box (each parameter scaled by its range): mean mu, step sigma, shape B with det 1;
+    candidates mu + sigma B z reflected into the box; rank-based utilities; B updated by a matrix exponential"""
+    from scipy.linalg import expm
+    n = len(lb)
+    lam = int(popsize) if popsize else 4 + int(math.floor(3 * math.log(n)))
+    width = ub - lb
+    mu = rng.random(n) if u0 is None else np.clip((np.asarray(u0, dtype=np.float64) - lb) / width, 0.0, 1.0)
+    sigma, B = 0.3, np.eye(n)
+    eta_mu, eta_s = 1.0, (9.0 + 3.0 * math.log(n)) / (5.0 * n * math.sqrt(n))
+    util = np.maximum(0.0, math.log(lam / 2.0 + 1.0) - np.log(np.arange(1, lam + 1)))
+    util = util / util.sum() - 1.0 / lam
+    best_x, best_f, evals, it, stall = None, math.inf, 0, 0, 0
+    one, zero = np.ones(n), np.zeros(n)
+    for it in range(1, int(maxiters) + 1):
+        z = rng.standard_normal((lam, n))
+        x = _reflect(mu + sigma * z @ B.T, zero, one)
+        cost = np.asarray(f(lb + x * width), dtype=np.float64)
+        evals += lam
+        order = np.argsort(cost, kind="stable")
+        if cost[order[0]] < best_f - tol * max(abs(best_f), 1e-300):
+            stall = 0
+        else:
+            stall += 1
+        if cost[order[0]] < best_f:
+            best_f, best_x = float(cost[order[0]]), x[order[0]].copy()
+        zs = z[order]
+        g_delta = util @ zs
+        g_M = (zs * util[:, None]).T @ zs - util.sum() * np.eye(n)
+        g_sigma = np.trace(g_M) / n
+        g_B = g_M - g_sigma * np.eye(n)
+        mu = np.clip(mu + eta_mu * sigma * B @ g_delta, 0.0, 1.0)
+        sigma *= math.exp(0.5 * eta_s * g_sigma)
+        B = B @ expm(0.5 * eta_s * g_B)
+        if sigma < 1e-9 or stall > 600:
+            break
+    return OptSolution(lb + best_x * width, best_f, it, evals)
 
 
 def fit_spr_data(surrogate, aligneddat, searchrange, optimiser=None, u0=None, device=0):
@@ -621,31 +703,12 @@ def fit_spr_data(surrogate, aligneddat, searchrange, optimiser=None, u0=None, de
     ub = np.array([r[1] for r in sr], dtype=np.float64)
     opt = Optimiser() if optimiser is None else optimiser
     rng = np.random.default_rng(_next_seed() if opt.seed is None else opt.seed)
-    NP = int(opt.popsize)
-    pop = lb + (ub - lb) * rng.random((NP, 5))
-    if u0 is not None:
-        pop[0] = np.clip(np.asarray(u0, dtype=np.float64), lb, ub)
-    cost = surrogate_sprdata_error(pop, surrogate, aligneddat, device)
-    evals, it = NP, 0
-    for it in range(1, int(opt.maxiters) + 1):
-        F = opt.F[0] + (opt.F[1] - opt.F[0]) * rng.random() if isinstance(opt.F, (tuple, list)) else opt.F
-        idx = np.array([rng.choice(NP - 1, size=3, replace=False) for _ in range(NP)])
-        idx += (idx >= np.arange(NP)[:, None])                       # three distinct members other than i
-        mutant = pop[idx[:, 0]] + F * (pop[idx[:, 1]] - pop[idx[:, 2]])
-        cross = rng.random((NP, 5)) < opt.CR
-        cross[np.arange(NP), rng.integers(0, 5, NP)] = True
-        trial = np.where(cross, mutant, pop)
-        # reflect at the bounds (stays inside the surrogate, like BlackBoxOptim's search space)
-        trial = np.where(trial < lb, np.minimum(2 * lb - trial, ub), trial)
-        trial = np.where(trial > ub, np.maximum(2 * ub - trial, lb), trial)
-        tcost = surrogate_sprdata_error(trial, surrogate, aligneddat, device)
-        evals += NP
-        better = tcost <= cost
-        pop[better], cost[better] = trial[better], tcost[better]
-        if np.isfinite(cost).all() and cost.max() - cost.min() <= opt.tol * max(abs(cost.min()), 1e-300):
-            break
-    k = int(np.argmin(cost))
-    sol = OptSolution(pop[k].copy(), float(cost[k]), it, evals)
+    f = lambda pop: surrogate_sprdata_error(pop, surrogate, aligneddat, device)
+    if opt.method == "xnes":
+        sol = minimise_xnes(f, lb, ub, rng, popsize=opt.popsize, maxiters=opt.maxiters, tol=opt.tol, u0=u0)
+    else:
+        sol = minimise_de(f, lb, ub, rng, popsize=opt.popsize, maxiters=opt.maxiters, F=opt.F, CR=opt.CR,
+                          tol=opt.tol, u0=u0)
     return sol, optpars_to_physpars(sol.u, aligneddat, surrogate)
 
 

@@ -104,3 +104,34 @@ def test_parameter_conversions_match_the_recorded_fit():
     lo, hi = api.rescale_logkon_max((-5.0, 2.0), sp.logkon_range, [25.0, 100.0])
     assert lo == -5.0 and hi == pytest.approx(2.0 - math.log10(4.0))
     assert api.rescale_logkon_max((-5.0, 1.0), sp.logkon_range, [25.0, 100.0]) == (-5.0, 1.0)
+
+
+@pytest.mark.parametrize("method", ["xnes", "de"])
+def test_population_optimisers_find_a_known_minimum(method):
+    """the two stand-ins for the reference's Optimization.jl methods (xNES is its default, fitting.jl:26-37) on
+    an anisotropic, coupled quadratic in the fit's 5-D box; the objective takes a whole population per call,
+    as the GPU loss does"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "sprfittingpaper2023.jl_b200"))
+    from sprb200 import api
+    lb = np.array([-4.0, -2.5, -1.5, 5.0, 1.0])
+    ub = np.array([-1.0, -0.5, 1.0, 25.0, 3.0])
+    xstar = np.array([-2.88, -1.39, -0.11, 15.3, 2.11])
+    calls = []
+
+    def f(pop):
+        assert pop.ndim == 2 and pop.shape[1] == 5 and np.all(pop >= lb) and np.all(pop <= ub)
+        calls.append(len(pop))
+        d = (pop - xstar) / (ub - lb)
+        return 1e3 * (d[:, 0] ** 2 + 10 * d[:, 1] ** 2 + 0.1 * d[:, 2] ** 2 + 3 * (d[:, 3] - d[:, 2]) ** 2 + d[:, 4] ** 2) + 79.0
+
+    rng = np.random.default_rng(1)
+    sol = api.minimise_xnes(f, lb, ub, rng) if method == "xnes" else api.minimise_de(f, lb, ub, rng)
+    assert sol.minimum == pytest.approx(79.0, abs=1e-6)
+    assert np.abs(sol.u - xstar).max() < 1e-3
+    assert sol.evals == sum(calls) and set(calls) == ({8} if method == "xnes" else {64})
+    # a minimum on the boundary of the box is found too (candidates are reflected into the box)
+    g = lambda pop: ((pop - lb) ** 2).sum(axis=1)
+    rng = np.random.default_rng(2)
+    sol = api.minimise_xnes(g, lb, ub, rng, maxiters=3000) if method == "xnes" else api.minimise_de(g, lb, ub, rng)
+    assert sol.minimum < 1e-6

@@ -58,8 +58,12 @@ def test_end_to_end_fit_recovers_the_documented_parameters(engine):
     loss_pub = api.surrogate_sprdata_error(pub, sur, ad)
     # the reference's own (finer, 100+ replicate) surrogate gives 78.99 at these parameters
     assert 60.0 < loss_pub < 130.0, loss_pub
-    sol, phys = api.fit_spr_data(sur, ad, [(1.5, 2.7)], optimiser=api.Optimiser(popsize=48, maxiters=300, seed=1))
+    sol, phys = api.fit_spr_data(sur, ad, [(1.5, 2.7)], optimiser=api.Optimiser("de", popsize=48, maxiters=300, seed=1))
     assert sol.minimum <= loss_pub + 1e-9
+    # xNES (the reference's default method) may stop in a local minimum; the best of a few starts cannot beat DE
+    # by more than noise and every start stays inside the table
+    xs = [api.fit_spr_data(sur, ad, [(1.5, 2.7)], optimiser=api.Optimiser("xnes", seed=k))[0] for k in range(4)]
+    assert all(np.isfinite(x.minimum) for x in xs) and min(x.minimum for x in xs) >= sol.minimum * (1 - 1e-3)
     pp = gold["physical_params"]
     # kon, koff and CP are well determined by the data; konb and reach trade off against each other
     assert phys[0] == pytest.approx(pp["kon"], rel=0.25)
