@@ -338,41 +338,9 @@ struct NbrRow {
     int o0, dg, j;   // first entry, degree, neighbour handled by this lane (valid if lane < dg)
 };
 
-// Experiment switches (scripts/build_variants.py builds one library per combination, scripts/run_variants.py
-// times them on the C2 build; results in profiles/README.md).  Defaults = the fastest measured combination:
-//   SPR_DEFER    apply the neighbour updates of an event after the next event's waiting time has been
-//                computed (hides the table-load latency, but the generic two-row update costs more than it saves)
-//   SPR_PREFETCH prefetch.global.L2 of the whole table at trajectory start (no gain: K2's records are still in L2)
-//   SPR_LDMODE   table loads: 0 generic, 1 ld.global, 2 ld.global.nc
-//   SPR_SCAN     shuffle scan with one early exit instead of five
-//   SPR_KBIT     k-th set bit of a ballot by a second ballot instead of a clear-lowest-bit loop
-#ifndef SPR_DEFER
-#define SPR_DEFER 0
-#endif
-#ifndef SPR_PREFETCH
-#define SPR_PREFETCH 0
-#endif
-#ifndef SPR_LDMODE
-#define SPR_LDMODE 2
-#endif
-#ifndef SPR_SCAN
-#define SPR_SCAN 1
-#endif
-#ifndef SPR_KBIT
-#define SPR_KBIT 1
-#endif
-
 // table entries are written by K2 (an earlier launch) and only read here
 __device__ __forceinline__ int ld_nbr(const uint16_t *__restrict__ nbr, uint32_t q) {
-#if SPR_LDMODE == 1
-    unsigned short v;
-    asm("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(nbr + q));
-    return (int)v;
-#elif SPR_LDMODE == 2
     return (int)__ldg(nbr + q);
-#else
-    return (int)nbr[q];
-#endif
 }
 
 template <typename OffT>
@@ -406,31 +374,6 @@ __device__ __forceinline__ void apply_row(SnT *sn, const uint16_t *__restrict__ 
 }
 
 // inclusive scan over the first nact (<= 32) lanes; the upper levels are skipped for short lists
-#if !SPR_SCAN
-__device__ __forceinline__ int scan_small(int v, int lane, int nact) {
-    if (nact > 1) {
-        int o = __shfl_up_sync(FULL, v, 1);
-        if (lane >= 1) v += o;
-        if (nact > 2) {
-            o = __shfl_up_sync(FULL, v, 2);
-            if (lane >= 2) v += o;
-            if (nact > 4) {
-                o = __shfl_up_sync(FULL, v, 4);
-                if (lane >= 4) v += o;
-                if (nact > 8) {
-                    o = __shfl_up_sync(FULL, v, 8);
-                    if (lane >= 8) v += o;
-                    if (nact > 16) {
-                        o = __shfl_up_sync(FULL, v, 16);
-                        if (lane >= 16) v += o;
-                    }
-                }
-            }
-        }
-    }
-    return v;
-}
-#else
 __device__ __forceinline__ int scan_small(int v, int lane, int nact) {
     int o = __shfl_up_sync(FULL, v, 1);
     if (lane >= 1) v += o;
@@ -446,12 +389,44 @@ __device__ __forceinline__ int scan_small(int v, int lane, int nact) {
     }
     return v;
 }
-#endif
+
+// GAP layout: the complex list lives in ab[cs .. cs+C), inside the gap between the A list (front) and the B
+// list (back) -- A + B + 2C = N, so the gap always holds 2C free slots -- instead of in an array of its own.
+// [lo, hi) is the gap as it will be once the list appends of the current event are done; the block is moved
+// (rarely: it is re-aligned to the side the gap is drifting away from) only when it would collide.
+__device__ __forceinline__ int cl_make_room(uint16_t *ab, int cs, int C, int lo, int hi, int lane) {
+    if (C == 0 || (cs >= lo && cs + C <= hi)) return cs;
+    const int ns = cs < lo ? hi - C : lo;
+    __syncwarp();                      // the uniform list writes of this event are visible to every lane
+    if (ns < cs) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            const int i = c0 + lane;
+            uint16_t v = 0;
+            if (i < C) v = ab[cs + i];
+            __syncwarp();
+            if (i < C) ab[ns + i] = v;
+            __syncwarp();
+        }
+    } else {
+#pragma unroll 1
+        for (int c0 = ((C - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
+            const int i = c0 + lane;
+            uint16_t v = 0;
+            if (i < C) v = ab[cs + i];
+            __syncwarp();
+            if (i < C) ab[ns + i] = v;
+            __syncwarp();
+        }
+    }
+    return ns;
+}
 
 // WPC = 5: 5 warps per CTA, 5 CTAs per SM (25 trajectories, 72 registers);
-// WPC = 4: 4 warps per CTA, 6 CTAs per SM (24 trajectories, 80 registers)
-template <typename SnT, typename OffT, int WPC>
-__global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(const TrajArgs a) {
+// WPC = 4: 4 warps per CTA, 6 CTAs per SM (24 trajectories, 80 registers);
+// WPC = 7 (GAP layout, 8 B of shared memory per particle): 7 warps per CTA, 4 CTAs per SM (28 trajectories)
+template <typename SnT, typename OffT, int WPC, bool GAP>
+__global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : (WPC == 7 ? 4 : 6)) spr_traj_kernel(const TrajArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using ST = SnTraits<SnT>;
     constexpr int SH_A = ST::SH_A, SH_B = ST::SH_B;
@@ -462,7 +437,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
     SnT *sn = reinterpret_cast<SnT *>(slice + a.lay.o_sn);
     uint16_t *ab = reinterpret_cast<uint16_t *>(slice + a.lay.o_ab);    // A from the front, B from the back
     uint16_t *pos = reinterpret_cast<uint16_t *>(slice + a.lay.o_pos);
-    uint16_t *cl = reinterpret_cast<uint16_t *>(slice + a.lay.o_cl);
+    uint16_t *cl = reinterpret_cast<uint16_t *>(slice + (GAP ? a.lay.o_ab : a.lay.o_cl));   // GAP: indexed from cs
     const int N = a.N, T = a.T;
     const int NB = N - 1;                                            // B-list element k lives at ab[NB - k]
     const double tstop = a.tstop, toff = a.toff;
@@ -488,13 +463,6 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
             reinterpret_cast<const uint16_t *>((uintptr_t)rec + (((size_t)(N + 1) * 4 + 15) & ~(size_t)15));
                 for (int i = lane; i <= N; i += 32) off[i] = (OffT)goff[i];
         __syncwarp();
-#if SPR_PREFETCH
-        {   // the entries were written by an earlier launch: pull them from HBM into L2 before the first event
-            const uint32_t nbytes = 2u * (uint32_t)off[N];
-            for (uint32_t o = 128u * (uint32_t)lane; o < nbytes; o += 128u * 32u)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char *>(nbr) + o));
-        }
-#endif
         // ---- initial state: everything A (forward_simulator.jl:148-149)
         for (int i = lane; i < N; i += 32) {
             const uint32_t deg = (uint32_t)off[i + 1] - (uint32_t)off[i];
@@ -505,6 +473,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
         __syncwarp();
 
         int cntA = N, cntB = 0, cntC = 0, nAB = 0;
+        int cs = 0;                                        // GAP layout: first slot of the complex list in ab
         double t = 0.0;
         double kon = pt.kon_eff;
         const double koff = pt.koff, konb = pt.konb;
@@ -526,13 +495,6 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
         // Neighbour updates of the previous event, applied only after the next event's waiting time and
         // channel have been computed (those need the counts alone): the global-memory latency of the rows
         // overlaps that arithmetic.  Row a takes da (+ 2 ds for the partner `oa`), row b db (+ ds for `ob`).
-#if SPR_DEFER
-        NbrRow pa, pb;
-        pa.o0 = pa.dg = pa.j = 0;
-        pb = pa;
-        uint32_t da = 0, db = 0, ds = 0;
-        int oa = -1, ob = -1;
-#endif
 
         for (;;) {
             if ((ndraw & 31u) == 0u) {
@@ -603,17 +565,6 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
 
             // ---- channel selection
             const double x = __dmul_rn(__dmul_rn((double)vz, 0x1.0p-32), a0);
-#define SPR_APPLY_PENDING()                                   \
-    do {                                                      \
-        apply_row<true, SnT>(sn, nbr, pa, da, oa, ds + ds, lane);   \
-        __syncwarp();                                         \
-        apply_row<true, SnT>(sn, nbr, pb, db, ob, ds, lane);        \
-        __syncwarp();                                         \
-    } while (0)
-#if SPR_DEFER
-            // ---- the previous event's neighbour updates land now (their loads were issued an event ago)
-            SPR_APPLY_PENDING();
-#endif
             if (x < cB) {
                 // A --> B (forward_simulator.jl:204-224) when x < cA, else B --> A (:228-253): the same
                 // code with the two lists swapped (A list: ab[k], B list: ab[NB - k])
@@ -627,25 +578,19 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 const int lastm = ab[fl];
                 ab[fk] = (uint16_t)lastm;
                 pos[lastm] = (uint16_t)k;
-                ab[tl] = (uint16_t)m;
-                pos[m] = (uint16_t)nto;
                 const int dAB = isab ? 1 : -1;
                 cntA -= dAB;
                 cntB += dAB;
+                if (GAP) cs = cl_make_room(ab, cs, cntC, cntA, N - cntB, lane);
+                ab[tl] = (uint16_t)m;
+                pos[m] = (uint16_t)nto;
                 const uint32_t v = sn[m];
                 nAB += dAB * ((int)((v >> SH_A) & CMASK) - (int)((v >> SH_B) & CMASK));
                 sn[m] = (SnT)((v & ~3u) | (isab ? ST_B : ST_A));       // idempotent: every lane stores the same word
                 const uint32_t dlt = (1u << SH_B) - (1u << SH_A);
-#if SPR_DEFER
-                pa = load_row<OffT>(nbr, off, m, lane);
-                pb.dg = 0;
-                da = isab ? dlt : 0u - dlt;
-                oa = -1;
-#else
                 const NbrRow rowm = load_row<OffT>(nbr, off, m, lane);
                 apply_row<false, SnT>(sn, nbr, rowm, isab ? dlt : 0u - dlt, 0, 0u, lane);
                 __syncwarp();
-#endif
             } else if (x < cP) {
                 // A + B --> C (:256-289): pair number k of the nAB active pairs, enumerated along the
                 // shorter of the A and B lists (weights nB resp. nA), then along the neighbour list.
@@ -664,11 +609,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                         w = (int)(((uint32_t)sn[xm] >> sh) & CMASK);
                     }
                     const int incl = scan_small(w, lane, nact);
-#if SPR_SCAN
                     const int tot = __shfl_sync(FULL, incl, nact - 1);
-#else
-                    const int tot = nact > 1 ? __shfl_sync(FULL, incl, nact - 1) : __shfl_sync(FULL, w, 0);
-#endif
                     if (k < tot) {
                         const uint32_t hit = __ballot_sync(FULL, k < incl);
                         const int Lh = __ffs(hit) - 1;
@@ -694,13 +635,8 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                         const uint32_t bal = __ballot_sync(FULL, ok);
                         const int c = __popc(bal);
                         if (k < c) {
-#if SPR_KBIT
                             // the lane holding set bit number k of the ballot
                             const uint32_t pick = __ballot_sync(FULL, ok && __popc(bal & lanemask_lt()) == k);
-#else
-                            uint32_t pick = bal;
-                            for (int r = 0; r < k; ++r) pick &= pick - 1u;
-#endif
                             ysel = __shfl_sync(FULL, j, __ffs(pick) - 1);
                             break;
                         }
@@ -721,7 +657,8 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                     ab[NB - ib] = (uint16_t)lastB;
                     pos[lastB] = (uint16_t)ib;
                     --cntB;
-                    cl[cntC] = (uint16_t)ma;
+                    if (GAP && cntC == 0) cs = cntA;       // the gap just opened: [cntA, N - cntB) holds 2 slots
+                    cl[cs + cntC] = (uint16_t)ma;
                     pos[ma] = (uint16_t)mb;
                     pos[mb] = (uint16_t)ma;
                     ++cntC;
@@ -729,16 +666,6 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 const uint32_t va = sn[ma], vb = sn[mb];
                 // a's neighbours lose an A neighbour, and b (one of them) drops B(2) -> C(0);
                 // b's neighbours lose a B neighbour, and a drops A(1) -> C(0)
-#if SPR_DEFER
-                pa = load_row<OffT>(nbr, off, ma, lane);
-                pb = load_row<OffT>(nbr, off, mb, lane);
-                nAB -= (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) - 1;
-                da = 0u - (1u << SH_A);
-                db = 0u - (1u << SH_B);
-                ds = 0u - 1u;
-                oa = mb;
-                ob = ma;
-#else
                 const NbrRow rowa = load_row<OffT>(nbr, off, ma, lane);
                 const NbrRow rowb = load_row<OffT>(nbr, off, mb, lane);
                 nAB -= (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) - 1;
@@ -747,14 +674,14 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 __syncwarp();
                 apply_row<true, SnT>(sn, nbr, rowb, 0u - (1u << SH_B), ma, 0u - 1u, lane);
                 __syncwarp();
-#endif
             } else {
                 // C --> A + B (:291-344): complex k; the freed end is chosen by a fair coin (:300-307)
                 const int k = (int)__umulhi(vw, (uint32_t)cntC);
-                int ma = cl[k];                      // the member that was A when the complex formed
+                int ma = cl[cs + k];                 // the member that was A when the complex formed
                 int mb = pos[ma];                    // its partner
-                cl[k] = cl[cntC - 1];
+                cl[cs + k] = cl[cs + cntC - 1];
                 --cntC;
+                if (GAP) cs = cl_make_room(ab, cs, cntC, cntA + 1, N - cntB - 1, lane);
                 if (vw & 1u) {
                     const int tmp = ma;
                     ma = mb;
@@ -769,16 +696,6 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 const uint32_t va = sn[ma], vb = sn[mb];
                 // a's neighbours gain an A neighbour, and b becomes B: C(0) -> B(2);
                 // b's neighbours gain a B neighbour, and a becomes A: C(0) -> A(1)
-#if SPR_DEFER
-                pa = load_row<OffT>(nbr, off, ma, lane);
-                pb = load_row<OffT>(nbr, off, mb, lane);
-                nAB += (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) + 1;
-                da = 1u << SH_A;
-                db = 1u << SH_B;
-                ds = 1u;
-                oa = mb;
-                ob = ma;
-#else
                 const NbrRow rowa = load_row<OffT>(nbr, off, ma, lane);
                 const NbrRow rowb = load_row<OffT>(nbr, off, mb, lane);
                 nAB += (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) + 1;
@@ -787,7 +704,6 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 __syncwarp();
                 apply_row<true, SnT>(sn, nbr, rowb, 1u << SH_B, ma, 1u, lane);
                 __syncwarp();
-#endif
             }
             if (last) break;
         }
@@ -1088,11 +1004,11 @@ cudaError_t set_table_attr(int bytes) {
     return cudaSuccess;
 }
 
-template <typename SnT, typename OffT, int WPC>
+template <typename SnT, typename OffT, int WPC, bool GAP>
 cudaError_t set_traj_attr(int bytes) {
     static int configured = -1;
     if (bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<SnT, OffT, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<SnT, OffT, WPC, GAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
         configured = bytes;
     }
@@ -1148,17 +1064,18 @@ bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int sm
     l.o_sn = o;   o += align16(N * (wide_sn ? 4 : 2));
     l.o_ab = o;   o += align16(N * 2);
     l.o_pos = o;  o += align16(N * 2);
-    l.o_cl = o;   o += align16((N / 2 + 1) * 2);
+    l.o_cl = o;
+    if (variant != 7) o += align16((N / 2 + 1) * 2);     // variant 7 keeps the complex list inside ab
     l.slice = o;
     // warps per CTA: most resident trajectories per SM (every CTA also costs 1 KB of reserved shared memory)
     int best = 0, best_w = 0, best_c = 0;
-    const int wmax = variant == 4 ? 4 : 5;
+    const int wmax = variant == 4 ? 4 : (variant == 7 ? 7 : 5);
     for (int w = 1; w <= wmax; ++w) {
         const long long bytes = (long long)w * l.slice;
         if (bytes > smem_optin) break;
         int c = (int)(smem_per_sm / (bytes + 1024));
         if (c > 32) c = 32;
-        const int regcap = (variant == 4 ? 24 : 25) / w;   // registers: at most 24 (80 regs) or 25 (72 regs) warps per SM
+        const int regcap = (variant == 4 ? 24 : (variant == 7 ? 28 : 25)) / w;   // warps per SM the register file allows
         if (c > regcap) c = regcap;
         if (c * w > best) { best = c * w; best_w = w; best_c = c; }
     }
@@ -1175,13 +1092,17 @@ cudaError_t launch_traj(const TrajArgs &a, int nblocks, cudaStream_t st) {
         using O_ = decltype(off_t);
         const int bytes = a.lay.slice * a.lay.wpc;
         if (a.lay.variant == 4) {
-            cudaError_t e = set_traj_attr<S_, O_, 4>(bytes);
+            cudaError_t e = set_traj_attr<S_, O_, 4, false>(bytes);
             if (e != cudaSuccess) return e;
-            spr_traj_kernel<S_, O_, 4><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+            spr_traj_kernel<S_, O_, 4, false><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+        } else if (a.lay.variant == 7) {
+            cudaError_t e = set_traj_attr<S_, O_, 7, true>(bytes);
+            if (e != cudaSuccess) return e;
+            spr_traj_kernel<S_, O_, 7, true><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
         } else {
-            cudaError_t e = set_traj_attr<S_, O_, 5>(bytes);
+            cudaError_t e = set_traj_attr<S_, O_, 5, false>(bytes);
             if (e != cudaSuccess) return e;
-            spr_traj_kernel<S_, O_, 5><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+            spr_traj_kernel<S_, O_, 5, false><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
         }
         return cudaGetLastError();
     });
