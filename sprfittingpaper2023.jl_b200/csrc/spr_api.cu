@@ -687,7 +687,7 @@ int sprb200_create(int device_ordinal, sprb200_handle *out) {
     }
     if (const char *env = std::getenv("SPRB200_MAX_WARPS")) h->max_warps = std::atoi(env);
     if (const char *env = std::getenv("SPRB200_STAGE_CAP")) h->stage_cap_override = std::atoi(env);
-    if (const char *env = std::getenv("SPRB200_K1_VARIANT")) { const int v = std::atoi(env); h->k1_variant = (v == 4 || v == 7) ? v : 5; }
+    if (const char *env = std::getenv("SPRB200_K1_VARIANT")) h->k1_variant = std::atoi(env) == 4 ? 4 : 5;
     if (const char *env = std::getenv("SPRB200_CAP_SCALE")) {
         const double v = std::atof(env);
         if (v > 0.0 && v <= 1.0) h->est_scale = v;

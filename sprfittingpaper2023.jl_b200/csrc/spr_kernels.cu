@@ -390,43 +390,11 @@ __device__ __forceinline__ int scan_small(int v, int lane, int nact) {
     return v;
 }
 
-// GAP layout: the complex list lives in ab[cs .. cs+C), inside the gap between the A list (front) and the B
-// list (back) -- A + B + 2C = N, so the gap always holds 2C free slots -- instead of in an array of its own.
-// [lo, hi) is the gap as it will be once the list appends of the current event are done; the block is moved
-// (rarely: it is re-aligned to the side the gap is drifting away from) only when it would collide.
-__device__ __forceinline__ int cl_make_room(uint16_t *ab, int cs, int C, int lo, int hi, int lane) {
-    if (C == 0 || (cs >= lo && cs + C <= hi)) return cs;
-    const int ns = cs < lo ? hi - C : lo;
-    __syncwarp();                      // the uniform list writes of this event are visible to every lane
-    if (ns < cs) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += 32) {
-            const int i = c0 + lane;
-            uint16_t v = 0;
-            if (i < C) v = ab[cs + i];
-            __syncwarp();
-            if (i < C) ab[ns + i] = v;
-            __syncwarp();
-        }
-    } else {
-#pragma unroll 1
-        for (int c0 = ((C - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
-            const int i = c0 + lane;
-            uint16_t v = 0;
-            if (i < C) v = ab[cs + i];
-            __syncwarp();
-            if (i < C) ab[ns + i] = v;
-            __syncwarp();
-        }
-    }
-    return ns;
-}
-
 // WPC = 5: 5 warps per CTA, 5 CTAs per SM (25 trajectories, 72 registers);
-// WPC = 4: 4 warps per CTA, 6 CTAs per SM (24 trajectories, 80 registers);
-// WPC = 7 (GAP layout, 8 B of shared memory per particle): 7 warps per CTA, 4 CTAs per SM (28 trajectories)
-template <typename SnT, typename OffT, int WPC, bool GAP>
-__global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : (WPC == 7 ? 4 : 6)) spr_traj_kernel(const TrajArgs a) {
+// WPC = 4: 4 warps per CTA, 6 CTAs per SM (24 trajectories, 80 registers: measured 1-3 % slower, kept as the
+// SPRB200_K1_VARIANT=4 experiment hook)
+template <typename SnT, typename OffT, int WPC>
+__global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(const TrajArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using ST = SnTraits<SnT>;
     constexpr int SH_A = ST::SH_A, SH_B = ST::SH_B;
@@ -437,7 +405,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : (WPC == 7 ? 4 : 6)) s
     SnT *sn = reinterpret_cast<SnT *>(slice + a.lay.o_sn);
     uint16_t *ab = reinterpret_cast<uint16_t *>(slice + a.lay.o_ab);    // A from the front, B from the back
     uint16_t *pos = reinterpret_cast<uint16_t *>(slice + a.lay.o_pos);
-    uint16_t *cl = reinterpret_cast<uint16_t *>(slice + (GAP ? a.lay.o_ab : a.lay.o_cl));   // GAP: indexed from cs
+    uint16_t *cl = reinterpret_cast<uint16_t *>(slice + a.lay.o_cl);
     const int N = a.N, T = a.T;
     const int NB = N - 1;                                            // B-list element k lives at ab[NB - k]
     const double tstop = a.tstop, toff = a.toff;
@@ -473,7 +441,6 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : (WPC == 7 ? 4 : 6)) s
         __syncwarp();
 
         int cntA = N, cntB = 0, cntC = 0, nAB = 0;
-        int cs = 0;                                        // GAP layout: first slot of the complex list in ab
         double t = 0.0;
         double kon = pt.kon_eff;
         const double koff = pt.koff, konb = pt.konb;
@@ -581,7 +548,6 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : (WPC == 7 ? 4 : 6)) s
                 const int dAB = isab ? 1 : -1;
                 cntA -= dAB;
                 cntB += dAB;
-                if (GAP) cs = cl_make_room(ab, cs, cntC, cntA, N - cntB, lane);
                 ab[tl] = (uint16_t)m;
                 pos[m] = (uint16_t)nto;
                 const uint32_t v = sn[m];
@@ -657,8 +623,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : (WPC == 7 ? 4 : 6)) s
                     ab[NB - ib] = (uint16_t)lastB;
                     pos[lastB] = (uint16_t)ib;
                     --cntB;
-                    if (GAP && cntC == 0) cs = cntA;       // the gap just opened: [cntA, N - cntB) holds 2 slots
-                    cl[cs + cntC] = (uint16_t)ma;
+                    cl[cntC] = (uint16_t)ma;
                     pos[ma] = (uint16_t)mb;
                     pos[mb] = (uint16_t)ma;
                     ++cntC;
@@ -677,11 +642,10 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : (WPC == 7 ? 4 : 6)) s
             } else {
                 // C --> A + B (:291-344): complex k; the freed end is chosen by a fair coin (:300-307)
                 const int k = (int)__umulhi(vw, (uint32_t)cntC);
-                int ma = cl[cs + k];                 // the member that was A when the complex formed
+                int ma = cl[k];                      // the member that was A when the complex formed
                 int mb = pos[ma];                    // its partner
-                cl[cs + k] = cl[cs + cntC - 1];
+                cl[k] = cl[cntC - 1];
                 --cntC;
-                if (GAP) cs = cl_make_room(ab, cs, cntC, cntA + 1, N - cntB - 1, lane);
                 if (vw & 1u) {
                     const int tmp = ma;
                     ma = mb;
@@ -1004,11 +968,11 @@ cudaError_t set_table_attr(int bytes) {
     return cudaSuccess;
 }
 
-template <typename SnT, typename OffT, int WPC, bool GAP>
+template <typename SnT, typename OffT, int WPC>
 cudaError_t set_traj_attr(int bytes) {
     static int configured = -1;
     if (bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<SnT, OffT, WPC, GAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<SnT, OffT, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
         configured = bytes;
     }
@@ -1064,18 +1028,17 @@ bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int sm
     l.o_sn = o;   o += align16(N * (wide_sn ? 4 : 2));
     l.o_ab = o;   o += align16(N * 2);
     l.o_pos = o;  o += align16(N * 2);
-    l.o_cl = o;
-    if (variant != 7) o += align16((N / 2 + 1) * 2);     // variant 7 keeps the complex list inside ab
+    l.o_cl = o;   o += align16((N / 2 + 1) * 2);
     l.slice = o;
     // warps per CTA: most resident trajectories per SM (every CTA also costs 1 KB of reserved shared memory)
     int best = 0, best_w = 0, best_c = 0;
-    const int wmax = variant == 4 ? 4 : (variant == 7 ? 7 : 5);
+    const int wmax = variant == 4 ? 4 : 5;
     for (int w = 1; w <= wmax; ++w) {
         const long long bytes = (long long)w * l.slice;
         if (bytes > smem_optin) break;
         int c = (int)(smem_per_sm / (bytes + 1024));
         if (c > 32) c = 32;
-        const int regcap = (variant == 4 ? 24 : (variant == 7 ? 28 : 25)) / w;   // warps per SM the register file allows
+        const int regcap = (variant == 4 ? 24 : 25) / w;   // registers: at most 24 (80 regs) or 25 (72 regs) warps per SM
         if (c > regcap) c = regcap;
         if (c * w > best) { best = c * w; best_w = w; best_c = c; }
     }
@@ -1092,17 +1055,13 @@ cudaError_t launch_traj(const TrajArgs &a, int nblocks, cudaStream_t st) {
         using O_ = decltype(off_t);
         const int bytes = a.lay.slice * a.lay.wpc;
         if (a.lay.variant == 4) {
-            cudaError_t e = set_traj_attr<S_, O_, 4, false>(bytes);
+            cudaError_t e = set_traj_attr<S_, O_, 4>(bytes);
             if (e != cudaSuccess) return e;
-            spr_traj_kernel<S_, O_, 4, false><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
-        } else if (a.lay.variant == 7) {
-            cudaError_t e = set_traj_attr<S_, O_, 7, true>(bytes);
-            if (e != cudaSuccess) return e;
-            spr_traj_kernel<S_, O_, 7, true><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+            spr_traj_kernel<S_, O_, 4><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
         } else {
-            cudaError_t e = set_traj_attr<S_, O_, 5, false>(bytes);
+            cudaError_t e = set_traj_attr<S_, O_, 5>(bytes);
             if (e != cudaSuccess) return e;
-            spr_traj_kernel<S_, O_, 5, false><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+            spr_traj_kernel<S_, O_, 5><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
         }
         return cudaGetLastError();
     });
