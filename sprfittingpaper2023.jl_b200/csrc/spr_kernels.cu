@@ -352,24 +352,44 @@ __device__ __forceinline__ NbrRow load_row(const uint16_t *__restrict__ nbr, con
     return r;
 }
 
-// sn[j] += delta for every neighbour j of the row; the neighbour `other` (the partner of a pair event,
-// -1 for none) also takes `extra`, its own state change: pair events need no separate state write.
+// sn[j] += delta for every neighbour j of the row; the neighbour `other` (the partner of a pair event)
+// also takes `extra`, its own state change: pair events need no separate state write.
+// apply_row covers the first 32 neighbours (one per lane), apply_row_tail the rest (degree > 32: rare).
 template <bool PAIR, typename SnT>
-__device__ __forceinline__ void apply_row(SnT *sn, const uint16_t *__restrict__ nbr, const NbrRow &r, uint32_t delta,
-                                          int other, uint32_t extra, int lane) {
+__device__ __forceinline__ void apply_row(SnT *sn, const NbrRow &r, uint32_t delta, int other, uint32_t extra, int lane) {
     if (lane < r.dg) {
         uint32_t d = delta;
         if (PAIR && r.j == other) d += extra;
         sn[r.j] = (SnT)((uint32_t)sn[r.j] + d);
     }
-    if (__builtin_expect(r.dg > 32, 0)) {
+}
+
+template <bool PAIR, typename SnT>
+__device__ __forceinline__ void apply_row_tail(SnT *sn, const uint16_t *__restrict__ nbr, const NbrRow &r, uint32_t delta,
+                                               int other, uint32_t extra, int lane) {
 #pragma unroll 1
-        for (int q = lane + 32; q < r.dg; q += 32) {
-            const int j = ld_nbr(nbr, (uint32_t)(r.o0 + q));
-            uint32_t d = delta;
-            if (PAIR && j == other) d += extra;
-            sn[j] = (SnT)((uint32_t)sn[j] + d);
-        }
+    for (int q = lane + 32; q < r.dg; q += 32) {
+        const int j = ld_nbr(nbr, (uint32_t)(r.o0 + q));
+        uint32_t d = delta;
+        if (PAIR && j == other) d += extra;
+        sn[j] = (SnT)((uint32_t)sn[j] + d);
+    }
+}
+
+// both rows of a pair event: every phase touches each state word at most once and the phases are separated
+// by __syncwarp(), so the order of the additions is immaterial; ONE uniform branch covers both tails
+template <typename SnT>
+__device__ __forceinline__ void apply_pair(SnT *sn, const uint16_t *__restrict__ nbr, const NbrRow &ra, const NbrRow &rb,
+                                           uint32_t da, uint32_t db, int ma, int mb, uint32_t ea, uint32_t eb, int lane) {
+    apply_row<true, SnT>(sn, ra, da, mb, ea, lane);
+    __syncwarp();
+    apply_row<true, SnT>(sn, rb, db, ma, eb, lane);
+    __syncwarp();
+    if (__builtin_expect((ra.dg | rb.dg) > 32, 0)) {
+        apply_row_tail<true, SnT>(sn, nbr, ra, da, mb, ea, lane);
+        __syncwarp();
+        apply_row_tail<true, SnT>(sn, nbr, rb, db, ma, eb, lane);
+        __syncwarp();
     }
 }
 
@@ -555,7 +575,8 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 sn[m] = (SnT)((v & ~3u) | (isab ? ST_B : ST_A));       // idempotent: every lane stores the same word
                 const uint32_t dlt = (1u << SH_B) - (1u << SH_A);
                 const NbrRow rowm = load_row<OffT>(nbr, off, m, lane);
-                apply_row<false, SnT>(sn, nbr, rowm, isab ? dlt : 0u - dlt, 0, 0u, lane);
+                apply_row<false, SnT>(sn, rowm, isab ? dlt : 0u - dlt, 0, 0u, lane);
+                if (__builtin_expect(rowm.dg > 32, 0)) apply_row_tail<false, SnT>(sn, nbr, rowm, isab ? dlt : 0u - dlt, 0, 0u, lane);
                 __syncwarp();
             } else if (x < cP) {
                 // A + B --> C (:256-289): pair number k of the nAB active pairs, enumerated along the
@@ -635,10 +656,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 const NbrRow rowb = load_row<OffT>(nbr, off, mb, lane);
                 nAB -= (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) - 1;
                 __syncwarp();   // every lane has read va, vb before the partner words change
-                apply_row<true, SnT>(sn, nbr, rowa, 0u - (1u << SH_A), mb, 0u - 2u, lane);
-                __syncwarp();
-                apply_row<true, SnT>(sn, nbr, rowb, 0u - (1u << SH_B), ma, 0u - 1u, lane);
-                __syncwarp();
+                apply_pair<SnT>(sn, nbr, rowa, rowb, 0u - (1u << SH_A), 0u - (1u << SH_B), ma, mb, 0u - 2u, 0u - 1u, lane);
             } else {
                 // C --> A + B (:291-344): complex k; the freed end is chosen by a fair coin (:300-307)
                 const int k = (int)__umulhi(vw, (uint32_t)cntC);
@@ -664,10 +682,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 const NbrRow rowb = load_row<OffT>(nbr, off, mb, lane);
                 nAB += (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) + 1;
                 __syncwarp();
-                apply_row<true, SnT>(sn, nbr, rowa, 1u << SH_A, mb, 2u, lane);
-                __syncwarp();
-                apply_row<true, SnT>(sn, nbr, rowb, 1u << SH_B, ma, 1u, lane);
-                __syncwarp();
+                apply_pair<SnT>(sn, nbr, rowa, rowb, 1u << SH_A, 1u << SH_B, ma, mb, 2u, 1u, lane);
             }
             if (last) break;
         }
