@@ -479,12 +479,10 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
         const int obs = a.observable;
         // randoms of 32 consecutive draws, one draw per lane: {E = -log U (double), w2, w3}
         uint32_t rEl = 0, rEh = 0, rz = 0, rw = 0;
-        // Neighbour updates of the previous event, applied only after the next event's waiting time and
-        // channel have been computed (those need the counts alone): the global-memory latency of the rows
-        // overlaps that arithmetic.  Row a takes da (+ 2 ds for the partner `oa`), row b db (+ ds for `ob`).
-
-        for (;;) {
-            if ((ndraw & 31u) == 0u) {
+        bool done = false;
+        while (!done) {
+            // 32 draws at a time, lane l holds draw ndraw + l (ndraw is a multiple of 32 here)
+            {
                 const u32x4 r = philox4x32_10(ndraw + (uint32_t)lane, STREAM_EVENTS, (uint32_t)rep, pidx,
                                               a.seed_lo, a.seed_hi);
                 const uint64_t k53 = (((uint64_t)r.x << 21) | (uint64_t)(r.y >> 11)) + 1ULL;
@@ -494,7 +492,8 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 rz = r.z;
                 rw = r.w;
             }
-            const int src = (int)(ndraw & 31u);
+#pragma unroll 1
+          for (int src = 0; src < 32; ++src) {
             const double E = __hiloint2double((int)__shfl_sync(FULL, rEh, src), (int)__shfl_sync(FULL, rEl, src));
             const uint32_t vz = __shfl_sync(FULL, rz, src);
             const uint32_t vw = __shfl_sync(FULL, rw, src);
@@ -505,11 +504,14 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
             const double cB = __dadd_rn(cA, __dmul_rn(koff, (double)cntB));
             const double cP = __dadd_rn(cB, __dmul_rn(konb, (double)nAB));
             const double a0 = __dadd_rn(cP, __dmul_rn(kc, (double)cntC));
-            double tn;
-            if (rcp_in_range(a0)) tn = __dadd_rn(t, event_dt_fast(E, a0));
-            else tn = a0 > 0.0 ? __dadd_rn(t, __ddiv_rn(E, a0)) : INF;
+            // the reciprocal-based waiting time is computed unconditionally; a total propensity outside its
+            // range (including 0: nothing can fire) is sorted out on the slow path, so that the common case
+            // takes ONE branch
+            const bool inrange = rcp_in_range(a0);
+            double tn = __dadd_rn(t, event_dt_fast(E, a0));
 
-            if (!(tn < tfast)) {
+            if (!(inrange && tn < tfast)) {
+                if (!inrange) tn = a0 > 0.0 ? __dadd_rn(t, __ddiv_rn(E, a0)) : INF;
                 // ---- slow path: antibody bath removed at tstop_AtoB (forward_simulator.jl:174-181,
                 // 199-202), save slots strictly before the next event keep the current state (:188-194)
                 bool switched = false;
@@ -543,6 +545,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 }
                 if (!(tn < INF)) {   // nothing can fire any more; all slots are filled
                     ++nskip;
+                    done = true;
                     break;
                 }
                 last = tn > tstop;   // the first event past tstop is still applied (:173, 183)
@@ -684,7 +687,11 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 __syncwarp();
                 apply_pair<SnT>(sn, nbr, rowa, rowb, 1u << SH_A, 1u << SH_B, ma, mb, 2u, 1u, lane);
             }
-            if (last) break;
+            if (last) {
+                done = true;
+                break;
+            }
+          }
         }
         // ---- remaining save slots take the final state (forward_simulator.jl:349-354)
         {
