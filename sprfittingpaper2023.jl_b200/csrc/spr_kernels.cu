@@ -546,7 +546,8 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 if (!(tn < INF)) {   // nothing can fire any more; all slots are filled
                     ++nskip;
                     done = true;
-                    break;
+                    src = 32;        // leaves the draw loop through its own condition (single-exit loop)
+                    continue;
                 }
                 last = tn > tstop;   // the first event past tstop is still applied (:173, 183)
                 tfast = fmin(fmin(tp, on ? toff : INF), tstop);
@@ -689,7 +690,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
             }
             if (last) {
                 done = true;
-                break;
+                src = 32;
             }
           }
         }
