@@ -229,9 +229,8 @@ def main():
         return 2
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL writes its version banner to stdout (NCCL_DEBUG=VERSION on some boxes): keep stdout to the JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # (with NCCL_DEBUG=VERSION in the environment NCCL prints its version banner to stdout at init; the JSON
+        # line below is always the LAST line of rank 0's stdout)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = sprb200.Engine(local_rank)
     L = _lib.domain_length(NPART, DIM)
