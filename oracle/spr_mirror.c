@@ -77,25 +77,10 @@ double spr_mirror_neg_log_u53(uint64_t k) {
 }
 
 /* ---------------------------------------------------------------- waiting time E / a0:
- * exponent-flip seed + four Newton steps + one multiply when the biased exponent of a0 is in
- * [64, 1984); plain IEEE division otherwise.  Returns t + dt (INFINITY when a0 == 0). */
+ * E times the correctly rounded reciprocal of a0 (two IEEE operations); a0 == 0 gives +inf. */
 double spr_mirror_next_time(double t, double E, double a0) {
-    uint64_t bits;
-    memcpy(&bits, &a0, 8);
-    uint32_t hi = (uint32_t)(bits >> 32);
-    /* device: (uint32)(hiint >> 20) with an arithmetic shift of the signed high word */
-    uint32_t ex = (uint32_t)(((int32_t)hi) >> 20);
-    if ((uint32_t)(ex - 64u) < 1920u) {
-        int64_t rb = (int64_t)0x7FDE6238DA3C2118LL - (int64_t)bits;
-        double r;
-        memcpy(&r, &rb, 8);
-        for (int it = 0; it < 4; it++) {
-            double e = fma(-a0, r, 1.0);
-            r = fma(r, e, r);
-        }
-        return t + E * r;
-    }
-    return a0 > 0.0 ? t + E / a0 : INFINITY;
+    const double r = 1.0 / a0;
+    return t + E * r;
 }
 
 /* ---------------------------------------------------------------- cell grid */

@@ -60,24 +60,10 @@ __device__ __forceinline__ double neg_log_u53(uint64_t k) {
 }
 
 // ---------------------------------------------------------------- waiting time dt = E / a0
-// Reciprocal by the exponent-flip seed r0 = bits^-1(K - bits(a0)) (5 % off) and four Newton steps
-// r <- r + r(1 - a0 r) (error 2.2e-16), then dt = E r.  Nine dependent double operations instead of
-// the ~23-instruction div.rn.f64 sequence; IEEE operations only, so the mirror reproduces it bit for bit.
-// Used when the biased exponent of a0 is in [64, 1984); otherwise (including a0 == 0) the caller falls
-// back to the plain IEEE division.
-constexpr long long RCP_MAGIC = 0x7FDE6238DA3C2118LL;
-__device__ __forceinline__ bool rcp_in_range(double a0) {
-    return ((uint32_t)(__double2hiint(a0) >> 20) - 64u) < 1920u;     // also false for a0 <= 0
-}
-__device__ __forceinline__ double event_dt_fast(double E, double a0) {
-    double r = __longlong_as_double(RCP_MAGIC - __double_as_longlong(a0));
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const double e = __fma_rn(-a0, r, 1.0);
-        r = __fma_rn(r, e, r);
-    }
-    return __dmul_rn(E, r);
-}
+// dt = E * RN(1 / a0): __drcp_rn (MUFU.RCP64H seed + 5 FMAs, correctly rounded, special cases in a
+// subroutine that is never reached for normal a0) and one multiply -- two IEEE operations, which the mirror
+// writes as E * (1.0 / a0).  a0 == 0 (nothing can fire) gives +inf.  Three dependent FMAs and five
+// instructions shorter than the exponent-flip seed + four Newton steps it replaced (specification v3).
 
 // ---------------------------------------------------------------- lattice positions
 // 21 bits per axis (top bits of one Philox word each), packed k0 | k1 << 21 | k2 << 42;

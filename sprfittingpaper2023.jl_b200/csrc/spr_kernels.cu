@@ -504,14 +504,11 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
             const double cB = __dadd_rn(cA, __dmul_rn(koff, (double)cntB));
             const double cP = __dadd_rn(cB, __dmul_rn(konb, (double)nAB));
             const double a0 = __dadd_rn(cP, __dmul_rn(kc, (double)cntC));
-            // the reciprocal-based waiting time is computed unconditionally; a total propensity outside its
-            // range (including 0: nothing can fire) is sorted out on the slow path, so that the common case
-            // takes ONE branch
-            const bool inrange = rcp_in_range(a0);
-            double tn = __dadd_rn(t, event_dt_fast(E, a0));
+            // waiting time E / a0 as E * RN(1 / a0) (IEEE reciprocal: MUFU.RCP64H seed + 5 FMAs); a0 == 0 gives
+            // +inf (nothing can fire), which the slow path sorts out
+            double tn = __dadd_rn(t, __dmul_rn(E, __drcp_rn(a0)));
 
-            if (!(inrange && tn < tfast)) {
-                if (!inrange) tn = a0 > 0.0 ? __dadd_rn(t, __ddiv_rn(E, a0)) : INF;
+            if (!(tn < tfast)) {
                 // ---- slow path: antibody bath removed at tstop_AtoB (forward_simulator.jl:174-181,
                 // 199-202), save slots strictly before the next event keep the current state (:188-194)
                 bool switched = false;
