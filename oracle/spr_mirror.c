@@ -286,9 +286,9 @@ int spr_mirror_trajectory(const MirrorSim *sim, double kon_eff, double koff, dou
         const uint64_t k53 = (((uint64_t)r[0] << 21) | (uint64_t)(r[1] >> 11)) + 1ULL;
         const double E = spr_mirror_neg_log_u53(k53);
         const double cA = kon * (double)cntA;
-        const double cB = cA + koff * (double)cntB;
-        const double cP = cB + konb * (double)nAB;
-        const double a0 = cP + kc * (double)cntC;
+        const double cB = fma(koff, (double)cntB, cA);
+        const double cP = fma(konb, (double)nAB, cB);
+        const double a0 = fma(kc, (double)cntC, cP);
         double tn = spr_mirror_next_time(t, E, a0);
         int switched = 0;
         if (on && tn >= toff) { tn = toff; switched = 1; }

@@ -501,9 +501,9 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
 
             // ---- total propensity (exact integer counts x rates)
             const double cA = __dmul_rn(kon, (double)cntA);
-            const double cB = __dadd_rn(cA, __dmul_rn(koff, (double)cntB));
-            const double cP = __dadd_rn(cB, __dmul_rn(konb, (double)nAB));
-            const double a0 = __dadd_rn(cP, __dmul_rn(kc, (double)cntC));
+            const double cB = __fma_rn(koff, (double)cntB, cA);
+            const double cP = __fma_rn(konb, (double)nAB, cB);
+            const double a0 = __fma_rn(kc, (double)cntC, cP);
             // waiting time E / a0 as E * RN(1 / a0) (IEEE reciprocal: MUFU.RCP64H seed + 5 FMAs); a0 == 0 gives
             // +inf (nothing can fire), which the slow path sorts out
             double tn = __dadd_rn(t, __dmul_rn(E, __drcp_rn(a0)));
