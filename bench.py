@@ -8,18 +8,30 @@ Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): ranges of
 /root/reference/examples/make_surrogate.jl:5-13 (log10 kon' -3..2, log10 koff -4..-1,
 log10 konb -3..1.5, reach 2..35 nm, tstop 600, tstop_AtoB 150, tsave = range(0,600,601)), default
 geometry (N = 1000, L = 236.686 nm, DIM 3, resampled positions), FIXED 100 replicates per point,
-size (10,10,10,10*N_gpus): 10^4 points = 10^6 trajectories PER GPU (weak scaling).  The linear
-grid points are dealt to the ranks in snake order of the library's a-priori cost estimate (every rank gets
-the same cost mix), each rank simulates its own points with no data-path collective, and one NCCL
-all-gather assembles the table, which is permuted on the device into the "FirstMoment" layout
-fitting.jl consumes.
+size (10,10,10,10*N_gpus): 10^4 points = 10^6 trajectories PER GPU (weak scaling).
 
-A step = one complete build.  `value` = SSA events/s with inputs resident (device API, output stays in
-HBM); `e2e` = the same through the host-buffer C-ABI call (H2D of the step's inputs, D2H of the
-table, inside the timed region).  Timing: CUDA events, barrier + synchronize on both sides, max over
-ranks.  One JSON line on stdout from rank 0.
+One process per GPU.  Every step is ONE call of the library's collective entry point
+sprb200_build_table_dist: the library deals the grid points to the ranks (snake order of its a-priori cost
+estimate), each rank simulates its share with no data-path collective, one ncclAllGather (bound by the
+library itself, not torch) assembles the mean-curve slabs and a device kernel permutes them into the
+"FirstMoment" layout fitting.jl consumes.  torch.distributed is used for the barrier and the max/sum of the
+timings only.
+
+A step = one complete build.  `value` = SSA events/s with the table left in HBM; `e2e` = the same call with
+a HOST table (H2D of the step's inputs, D2H of the table, inside the timed region), over all K steps.
+Secondary blocks in the same JSON line: `strong` (a FIXED-size job -- a 14x10x10x10 lattice over the
+paper-scale C3 ranges with the reference's VarianceTerminator(0.01,15,250) -- split over the N ranks, with
+the sha256 of the gathered table: identical for every N), `c3_sample` (that job projected to the full
+1,512,000-point grid, next to the CPU port timed on a stratified sample of the same lattice, N=1 only),
+`small_batch` (BASELINE configs 0 and 3 with the reference's nsims = 1000).
+Timing: CUDA events, barrier + synchronize on both sides, max over ranks.  One JSON line on stdout from rank 0.
+
+--impl reference: the reference's own CPU implementation of the path (oracle/spr_ref.c: the reference is Julia
+and cannot run here), compiled on this machine with -O3 -march=native, all host threads, a stratified bounded
+sample of the C2 grid per step.  Imports nothing of the product (grid and strata are computed in numpy).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -29,9 +41,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "sprfittingpaper2023.jl_b200")
-for _p in (ROOT, PKG):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
 
 import numpy as np  # noqa: E402
 
@@ -47,6 +56,13 @@ UNIT = "events/s"
 ISSUE_PER_CLK = 148 * 4          # warp-instructions per clock, chip-wide
 SMEM_B_PER_CLK = 148 * 128       # shared-memory bytes per clock, chip-wide
 I_ALG = 170.0                    # flat-scan algorithmic warp-instructions per event at N=1000
+# paper-scale grid (examples/cluster_scripts/make_surrogate_metadata.jl:12-23) and the fixed-size lattice over
+# the same ranges used for the strong-scaling / C3 blocks (0.93 % of its 1,512,000 points, corners included)
+C3_RANGES = dict(logkon=(-5.0, 2.0), logkoff=(-4.0, 0.0), logkonb=(-3.0, 1.5), reach=(2.0, 35.0))
+C3_SIZE = (42, 40, 30, 30)
+C3_LATTICE = (14, 10, 10, 10)
+C3_TERM = (0.01, 15, 250)
+L_DEFAULT = (NPART / (6.02214076e-7 * (500 / 149 / 26795 * 1000000))) ** (1.0 / 3.0)   # parameters.jl:4,138-139
 
 
 def config(world):
@@ -56,31 +72,110 @@ def config(world):
         "points_per_gpu": NK[0] * NK[1] * NK[2] * NREACH_PER_GPU,
         "replicates": NREP,
         "trajectories_per_gpu": NK[0] * NK[1] * NK[2] * NREACH_PER_GPU * NREP,
-        "sharding": "grid points dealt to ranks in snake order of the a-priori cost estimate (equal cost mix per rank); "
-                    "NCCL all-gather of the mean-curve slabs only",
+        "sharding": "sprb200_build_table_dist: grid points dealt to ranks in snake order of the a-priori cost estimate "
+                    "(equal cost mix per rank); one ncclAllGather of the mean-curve slabs",
         "l2": "no flush needed: every step streams >1.2 GB of replicate curves per GPU (L2 is 126 MB) and all "
               "trajectory state lives in shared memory",
         "seed": SEED,
     }
 
 
-_deal_cache = {}
+# ------------------------------------------------------------------------------------------------
+# numpy statement of the grids (surrogate.jl:208-211, 284) and of an a-priori cost used ONLY to stratify the
+# CPU samples -- the reference arm imports nothing of the product
+def grid_points_np(ranges, size):
+    """[P][4] kon', koff, konb, reach of the column-major linear index order (kon fastest)"""
+    ax = [np.linspace(ranges[k][0], ranges[k][1], size[i]) for i, k in enumerate(("logkon", "logkoff", "logkonb", "reach"))]
+    i1, i2, i3, i4 = np.meshgrid(*[np.arange(n) for n in size], indexing="ij")
+    order = lambda a: a.reshape(-1, order="F")
+    return np.stack([10.0 ** ax[0][order(i1)], 10.0 ** ax[1][order(i2)], 10.0 ** ax[2][order(i3)], ax[3][order(i4)]], axis=1)
 
 
-def rank_indices(world, rank):
-    """1-based linear indices of this rank.  Cost-balanced deal: the grid points, sorted by the library's
-    a-priori cost estimate, are handed to the ranks in snake order, so every rank simulates the same
-    mix of cheap and expensive points (a block-cyclic deal by reach value left the last rank 5 % more
-    work at 8 GPUs: profiles/r1_bench_c2_8gpu_blockcyclic.json)."""
-    if world not in _deal_cache:
-        from sprb200 import _lib
-        import sprb200
-        grid = _lib.make_grid(RANGES["logkon"], RANGES["logkoff"], RANGES["logkonb"], RANGES["reach"],
-                              NK + (NREACH_PER_GPU * world,))
-        sim = sprb200.SimSpec(NPART, DIM, _lib.domain_length(NPART, DIM), TSTOP, TOFF, np.linspace(0.0, TSTOP, NT))
-        cost = _lib.estimate_cost(sim, _lib.grid_points(grid))
-        _deal_cache[world] = [d + 1 for d in _lib.balanced_deal(cost, world)]
-    return _deal_cache[world][rank]
+def apriori_events(pts, tstop=TSTOP, toff=TOFF, N=NPART, L=L_DEFAULT):
+    """rough SSA events of one replicate (first-order kinetics + pair re-formation), for stratification only"""
+    kon, koff, konb, reach = pts.T
+    ta, td = min(max(toff, 0.0), tstop), tstop - min(max(toff, 0.0), tstop)
+    deg = np.minimum(N - 1.0, (N - 1.0) * np.minimum(4.0 / 3.0 * np.pi * reach ** 3 / L ** 3, 1.0))
+    bound = kon * ta / (1.0 + kon * ta)
+    cyc = kon * koff / (kon + koff)
+    ev = N * (np.minimum(1.0, kon * ta) + 2.0 * cyc * ta + bound * np.minimum(1.0, koff * td))
+    pre = konb / (konb + koff)
+    ev = ev + N * np.minimum(1.0, deg) * bound * 2.0 * koff * tstop * pre * (1.0 + 4.0 * pre)
+    return ev + 600.0, deg
+
+
+class CpuPort:
+    """oracle/spr_ref.c built natively on this machine, timed per point with all host threads busy"""
+
+    def __init__(self):
+        sys.path.insert(0, ROOT)
+        from oracle import ref_oracle as R
+        self.R = R
+        self.L = R.build_native()
+        self.ncores = os.cpu_count() or 1
+
+    def rate(self, pts_all, ev_prior, deg_prior, sample_seed, run_seed, term=None, nrep_full=NREP, nstrata=16,
+             budget_core_s=None, point_cap_s=1.5):
+        """projected events/s of the WHOLE workload `pts_all` on all host threads, from a stratified sample.
+
+        Strata hold equal shares of the a-priori cost; inside a stratum the points are drawn uniformly and the
+        stratum totals are ratio estimates with the a-priori cost as auxiliary variable (total = prior total x
+        sampled measured / sampled prior), for seconds and for events separately.  FIXED terminator: the replicates
+        of a sampled point are truncated to `point_cap_s` of CPU time (the rate per event does not depend on the
+        replicate count).  Variance terminator: the stopping rule decides the replicates, nothing is truncated."""
+        R = self.R
+        ncores = self.ncores
+        budget = budget_core_s or 54.0 * ncores
+        rng = np.random.default_rng(sample_seed)
+        sec_prior = ev_prior * (1.0 + deg_prior / 32.0) * 5.0e-7 + 5.5e-3   # per replicate: event work + O(N^2) setup (calibrated on 8 cores)
+        reps_prior = nrep_full if term is None else 190.0
+        pt_cost = np.minimum(point_cap_s, sec_prior * reps_prior) if term is None else sec_prior * reps_prior
+        order = np.argsort(sec_prior, kind="stable")
+        csum = np.cumsum(sec_prior[order])
+        edges = np.searchsorted(csum, csum[-1] * np.arange(1, nstrata) / nstrata)
+        strata = []
+        for members in np.split(order, edges):
+            if len(members) == 0:
+                continue
+            m = int(np.clip(budget / nstrata / pt_cost[members].mean(), 4, min(len(members), 96)))
+            strata.append((members, rng.choice(members, size=min(m, len(members)), replace=False)))
+        sel = np.concatenate([s for _, s in strata])
+        if term is None:
+            nsims = np.clip(np.floor(point_cap_s / sec_prior[sel]), 10, nrep_full).astype(np.int32)
+            cterm = R.make_term("number")
+        else:
+            nsims = None
+            cterm = R.make_term("variance", *term)
+        sim = R.make_sim(N=NPART, DIM=DIM, tstop=TSTOP, tstop_AtoB=TOFF, tsave=np.linspace(0.0, TSTOP, NT), nsims=nrep_full)
+        # expensive points first: the dynamic queue then ends on cheap ones (short tail)
+        o = np.argsort(-pt_cost[sel], kind="stable")
+        nobs, nev, secs, wall = R.run_points_timed(pts_all[sel][o], sim, cterm, None if nsims is None else nsims[o],
+                                                   seed=run_seed, streams=sel[o], nthreads=ncores, L=self.L)
+        inv = np.empty_like(o); inv[o] = np.arange(len(o))
+        nobs, nev, secs = nobs[inv].astype(np.float64), nev[inv].astype(np.float64), secs[inv]
+        tot_ev = tot_cs = 0.0
+        k = 0
+        for members, s in strata:
+            m = len(s)
+            e, t, n = nev[k:k + m], secs[k:k + m], nobs[k:k + m]
+            k += m
+            scale = nrep_full / n if term is None else np.ones(m)      # to the full replicate count of the workload
+            tot_cs += sec_prior[members].sum() * (t * scale).sum() / sec_prior[s].sum()
+            tot_ev += ev_prior[members].sum() * (e * scale).sum() / ev_prior[s].sum()
+        return dict(value=tot_ev / (tot_cs / ncores), events_total=tot_ev, core_seconds_total=tot_cs,
+                    wall_projected=tot_cs / ncores, sample_points=int(len(sel)), sample_wall=wall,
+                    sample_core_seconds=float(secs.sum()), sample_events=float(nev.sum()),
+                    busy=float(secs.sum() / (wall * ncores)), nstrata=len(strata), truncated=term is None)
+
+
+def sample_text(r, what):
+    return ("%d of the %s points, stratified: %d strata of equal a-priori cost, ratio estimate per stratum, %s; per-point "
+            "thread seconds with all %d host threads busy (busy fraction %.2f), scaled to the whole workload; "
+            "oracle/spr_ref.c = restatement of forward_simulator.jl (heap next-reaction SSA, O(N^2) setup per "
+            "replicate), gcc -O3 -march=native built on this machine"
+            % (r["sample_points"], what, r["nstrata"],
+               "replicates truncated to equal CPU time per point" if r["truncated"] else "full stopping rule",
+               os.cpu_count() or 1, r["busy"]))
 
 
 def mean_degree(reach, L):
@@ -140,40 +235,44 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ------------------------------------------------------------------------------------------------
-def cpu_sample(ncores, seed):
-    """Bounded sample of the same workload for the CPU legs: 12 points per host thread drawn uniformly
-    (seeded) from the 10^4-point C2 grid, 100 replicates each (about 10-20 s on all cores)."""
-    from sprb200 import _lib
-    grid = _lib.make_grid(RANGES["logkon"], RANGES["logkoff"], RANGES["logkonb"], RANGES["reach"],
-                          NK + (NREACH_PER_GPU,))
-    P = NK[0] * NK[1] * NK[2] * NREACH_PER_GPU
-    npts = int(min(P, max(16, 12 * ncores)))
-    rng = np.random.default_rng(seed)
-    idx = np.sort(rng.choice(P, size=npts, replace=False)) + 1
-    import ctypes as C
-    L = _lib.load()
-    pts = np.zeros((npts, 4))
-    p = _lib.SprPoint()
-    for k, i in enumerate(idx):
-        L.sprb200_grid_point(C.byref(grid), int(i), C.byref(p))
-        pts[k] = (p.kon_eff, p.koff, p.konb, p.reach)
-    return idx, pts
+def reference_arm(args, K, W):
+    """the reference's CPU implementation on the box's host cores; never touches the product or the GPU"""
+    cpu = CpuPort()
+    pts = grid_points_np(RANGES, NK + (NREACH_PER_GPU,))
+    ev, deg = apriori_events(pts)
+    for w in range(W):
+        cpu.rate(pts, ev, deg, 900 + w, 1000 + w, budget_core_s=4.0 * cpu.ncores)
+    vals, secs, rs = [], 0.0, []
+    for k in range(K):
+        r = cpu.rate(pts, ev, deg, 777 + k, 2000 + k)
+        vals.append(r["value"]); secs += r["sample_wall"]; rs.append(r)
+    val = float(np.mean(vals))
+    cfg = config(1)
+    cfg["reference_sample_points_per_step"] = rs[0]["sample_points"]
+    cfg["reference_sample_events_per_step"] = rs[0]["sample_events"]
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "per_step_values": vals, "spread": float((max(vals) - min(vals)) / val),
+        "projected_c2_build_seconds": float(np.mean([r["wall_projected"] for r in rs])),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cpu.ncores, "kind": "port",
+                         "sample": sample_text(rs[0], "10^4 C2 grid")},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
 
 
-def run_cpu_reference(ncores, seed, pts=None, idx=None):
-    """The reference's algorithm (oracle/spr_ref.c: next-reaction heap, O(N^2) setup per replicate), one
-    thread per host core over parameter points -- the reference's own parallelism (independent index
-    ranges, examples/cluster_scripts/queue_job.sh:10-17)."""
-    from oracle import ref_oracle as R
-    if pts is None:
-        idx, pts = cpu_sample(ncores, 777)
-    sim = R.make_sim(N=NPART, DIM=DIM, tstop=TSTOP, tstop_AtoB=TOFF, tsave=np.linspace(0.0, TSTOP, NT), nsims=NREP)
-    term = R.make_term("number")
-    t0 = time.perf_counter()
-    _, nobs, nev = R.run_points(pts, sim, term, seed=seed, streams=idx - 1, nthreads=ncores)
-    dt = time.perf_counter() - t0
-    return dict(events=int(nev.sum()), trajectories=int(nobs.sum()), seconds=dt, points=len(pts))
+def measured_profile():
+    """ncu counters of the dominant kernel for the committed code (profiles/r2_ncu_k1.json, written from the
+    ncu --set full capture by scripts/ncu_summary.py): executed-issue fraction, instructions per event, DRAM bytes"""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_k1.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 def main():
@@ -183,6 +282,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the strong / c3_sample / small_batch blocks")
     args = ap.parse_args()
     K, W = max(1, args.steps), max(0, args.warmup)
     rank = int(os.environ.get("RANK", "0"))
@@ -191,34 +291,14 @@ def main():
     ncores = os.cpu_count() or 1
 
     if args.impl == "reference":
-        # the reference's own CPU implementation of the path (restated: Julia cannot run in this image),
-        # all host threads, bounded sample of the same workload; rank 0 only
         if rank != 0:
             return 0
-        from oracle import ref_oracle as R
-        R.build()
-        idx, pts = cpu_sample(ncores, 777)
-        for w in range(W):
-            run_cpu_reference(ncores, 1000 + w, pts, idx)
-        ev = tr = 0
-        secs = 0.0
-        for k in range(K):
-            r = run_cpu_reference(ncores, 2000 + k, pts, idx)
-            ev += r["events"]; tr += r["trajectories"]; secs += r["seconds"]
-        val = ev / secs
-        sample = ("%d of the 10^4 C2 grid points (seeded uniform subset) x %d replicates per step; restatement of "
-                  "forward_simulator.jl (heap next-reaction SSA, O(N^2) setup per replicate), gcc -O3" % (len(pts), NREP))
-        print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
-            "warmup": W, "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(args.gpus),
-            "trajectories_per_sec": tr / secs,
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
-        return 0
+        return reference_arm(args, K, W)
 
     # ------------------------------------------------------------------ our arm
+    for _p in (ROOT, PKG):
+        if _p not in sys.path:
+            sys.path.insert(0, _p)
     import torch
     import torch.distributed as dist
     import sprb200
@@ -228,24 +308,27 @@ def main():
         sys.stderr.write("bench.py: no CUDA device; the product has no CPU path\n")
         return 2
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
         # (with NCCL_DEBUG=VERSION in the environment NCCL prints its version banner to stdout at init; the JSON
         # line below is always the LAST line of rank 0's stdout)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
     eng = sprb200.Engine(local_rank)
+    # the library's own communicator: rank 0 creates the id, torch.distributed only carries the 128 bytes
+    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if world > 1:
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(_lib.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+    eng.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank)
+
     L = _lib.domain_length(NPART, DIM)
     tsave = np.linspace(0.0, TSTOP, NT)
     sim = sprb200.SimSpec(NPART, DIM, L, TSTOP, TOFF, tsave)
-    grid = _lib.make_grid(RANGES["logkon"], RANGES["logkoff"], RANGES["logkonb"], RANGES["reach"],
-                          NK + (NREACH_PER_GPU * world,))
-    P = NK[0] * NK[1] * NK[2] * NREACH_PER_GPU * world
-    idx = rank_indices(world, rank)
-    idx_all = np.concatenate([rank_indices(world, r) for r in range(world)])
-    count = len(idx)
-    dev = torch.device("cuda", local_rank)
-    rows = torch.empty((count, NT), dtype=torch.float64, device=dev)
-    nev_d = torch.zeros(count, dtype=torch.int64, device=dev)
-    all_rows = torch.empty((count * world, NT), dtype=torch.float64, device=dev) if world > 1 else rows
+    size4 = NK + (NREACH_PER_GPU * world,)
+    grid = _lib.make_grid(RANGES["logkon"], RANGES["logkoff"], RANGES["logkonb"], RANGES["reach"], size4)
+    P = int(np.prod(size4))
+    count = len(_lib.deal_indices(grid, sim, world, rank))
     table = torch.empty((NT, P), dtype=torch.float64, device=dev)
 
     def barrier():
@@ -253,29 +336,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches = [0]
-    build_ms = [0.0]
-    traj_ms = [0.0]
-    table_ms = [0.0]
-    events_step = [0]
+    acc = dict(launches=0, build_ms=0.0, traj_ms=0.0, table_ms=0.0, events=0)
 
     def step(seed):
         run = _lib.make_run(nsims=NREP, seed=seed)
-        eng.build_indices_device(grid, sim, run, idx, rows.data_ptr(), 0, nev_d.data_ptr())
+        eng.build_table_dist(grid, sim, run, host=False, d_table=table.data_ptr(), want_counts=False)
         st = eng.stats()
-        launches[0] += st["kernel_launches"] + 1
-        build_ms[0] += st["device_ms"]
-        traj_ms[0] += st["traj_ms"]
-        table_ms[0] += st["table_ms"]
-        events_step[0] += st["events"]
-        if world > 1:
-            dist.all_gather_into_tensor(all_rows, rows)
-            torch.cuda.synchronize()
-        eng.scatter_rows_device(all_rows.data_ptr(), idx_all, NT, P, table.data_ptr())
+        acc["launches"] += st["kernel_launches"]
+        acc["build_ms"] += st["device_ms"]
+        acc["traj_ms"] += st["traj_ms"]
+        acc["table_ms"] += st["table_ms"]
+        acc["events"] += st["events"]
 
     for w in range(W):
         step(SEED + 100 + w)
-    launches[0] = 0; build_ms[0] = 0.0; traj_ms[0] = 0.0; table_ms[0] = 0.0; events_step[0] = 0
+    for k in acc:
+        acc[k] = 0
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -290,76 +366,128 @@ def main():
     ms = e0.elapsed_time(e1)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    nev_host = nev_d.cpu().numpy().astype(np.float64)          # last step's per-point events (this rank)
 
-    # whole-job numbers: max time over ranks, events summed over ranks
-    tms = torch.tensor([ms, build_ms[0], traj_ms[0], table_ms[0]], dtype=torch.float64, device=dev)
-    tev = torch.tensor([float(events_step[0]), float(launches[0])], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tev, op=dist.ReduceOp.SUM)
-    ms_total, build_ms_total, traj_ms_total, table_ms_total = float(tms[0]), float(tms[1]), float(tms[2]), float(tms[3])
-    ev_total, launches_total = float(tev[0]), int(tev[1])
+    def allreduce(vals, op):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return [float(x) for x in t]
+
+    MAX, SUM, MIN = (dist.ReduceOp.MAX, dist.ReduceOp.SUM, dist.ReduceOp.MIN)
+    ms_total, build_ms_total, traj_ms_total, table_ms_total = allreduce([ms, acc["build_ms"], acc["traj_ms"], acc["table_ms"]], MAX)
+    traj_ms_min, = allreduce([acc["traj_ms"]], MIN)
+    ev_total, launches_total = allreduce([float(acc["events"]), float(acc["launches"])], SUM)
     value = ev_total / (ms_total * 1e-3)
-    traj_total = count * NREP * world * K
+    traj_total = P * NREP * K
 
-    # ---- end to end through the host-buffer C-ABI call (H2D inputs + D2H results inside the region)
+    # ---- end to end through the host-buffer call (H2D inputs + D2H of the table inside the region), all K steps
     def e2e_step(seed):
         run = _lib.make_run(nsims=NREP, seed=seed)
-        out, nu, nev = eng.build_indices(grid, sim, run, idx)
-        return int(nev.sum())
+        tab, nu, nev = eng.build_table_dist(grid, sim, run, host=(rank == 0), want_counts=(rank == 0))
+        return eng.stats()["events"]
 
     e2e_step(SEED + 50)
     barrier()
     t0 = time.perf_counter()
     ev_e2e = 0
-    E2E_STEPS = max(1, min(K, 2))
-    for k in range(E2E_STEPS):
+    for k in range(K):
         ev_e2e += e2e_step(SEED + 60 + k)
     torch.cuda.synchronize()
-    dt_e2e = time.perf_counter() - t0
-    te = torch.tensor([dt_e2e], dtype=torch.float64, device=dev)
-    tv = torch.tensor([float(ev_e2e)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tv, op=dist.ReduceOp.SUM)
-    e2e_val = float(tv[0]) / float(te[0])
-    h2d = count * (32 + 4 + 8) + NT * 8                 # points, RNG indices, work order, tsave
-    d2h = count * NT * 8 + count * (4 + 8 + 8)          # mean curves, n_used, n_events (+ internal counters)
+    dt_e2e, = allreduce([time.perf_counter() - t0], MAX)
+    ev_e2e_tot, = allreduce([float(ev_e2e)], SUM)
+    e2e_val = ev_e2e_tot / dt_e2e
+    h2d = world * (count * (32 + 4 + 8) + NT * 8 + count * world * 8)  # points, RNG indices, work order, tsave, gather index list
+    d2h = P * NT * 8 + P * (4 + 8) + world * count * 8                 # table + n_used + n_events on rank 0; per-rank event counters
+
+    # ---- secondary blocks ---------------------------------------------------------------------------------
+    strong = c3 = small = None
+    if not args.no_secondary:
+        # fixed-size job split over the ranks (strong scaling) + hash of the gathered table (same for every N)
+        g3 = _lib.make_grid(C3_RANGES["logkon"], C3_RANGES["logkoff"], C3_RANGES["logkonb"], C3_RANGES["reach"], C3_LATTICE)
+        run3 = _lib.make_run(variance=C3_TERM, seed=SEED)
+        eng.build_table_dist(_lib.make_grid(C3_RANGES["logkon"], C3_RANGES["logkoff"], C3_RANGES["logkonb"],
+                                            C3_RANGES["reach"], (2, 2, 2, 2 * world)), sim, run3, host=False, want_counts=False)
+        barrier()
+        s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+        s0.record()
+        tab3, nu3, nev3 = eng.build_table_dist(g3, sim, run3, host=(rank == 0), want_counts=(rank == 0))
+        s1.record()
+        torch.cuda.synchronize()
+        st3 = eng.stats()
+        strong_ms, k1_3 = allreduce([s0.elapsed_time(s1), st3["traj_ms"]], MAX)
+        k1_3_min, = allreduce([st3["traj_ms"]], MIN)
+        if rank == 0:
+            P3, PF = int(np.prod(C3_LATTICE)), int(np.prod(C3_SIZE))
+            strong = {
+                "workload": "14x10x10x10 lattice over the paper-scale ranges (make_surrogate_metadata.jl:12-23), "
+                            "VarianceTerminator(0.01,15,250), N=1000, 601 save times; FIXED total work split over the ranks",
+                "scaling": "strong", "points": P3, "strong_ms": strong_ms, "events": int(nev3.sum()),
+                "trajectories_run": int(st3["trajectories"]) if world == 1 else None,
+                "replicates_used_mean": float(nu3.mean()), "events_per_sec": float(nev3.sum()) / (strong_ms * 1e-3),
+                "k1_ms_slowest_rank": k1_3, "k1_ms_fastest_rank": k1_3_min,
+                "table_sha256": hashlib.sha256(np.ascontiguousarray(tab3).tobytes()).hexdigest(),
+                "n_used_sha256": hashlib.sha256(np.ascontiguousarray(nu3).tobytes()).hexdigest(),
+            }
+            c3 = {
+                "what": "paper-scale build (42x40x30x30 = 1,512,000 points, VarianceTerminator(0.01,15,250)) projected from "
+                        "the lattice above: seconds x %d/%d" % (PF, P3),
+                "gpu_projected_full_build_s": strong_ms * 1e-3 * PF / P3, "n_gpus": world,
+            }
+        # small-batch regime (BASELINE configs 0 and 3 with the reference's nsims = 1000)
+        if rank == 0:
+            small = {}
+            cases = {"C1_default_reach30_25nM_nsims1000": ([10 ** -2.8789331867029184, 10 ** -1.3886105070021626,
+                                                            10 ** -0.107804350729586, 30.0], L, 600.0),
+                     "C4b_reach50_2x_density_nsims1000": ([1.0, 0.1, 1.0, 50.0], 187.86, 300.0)}
+            for nm, (pt, Lc, ts) in cases.items():
+                simc = sprb200.SimSpec(NPART, DIM, Lc, ts, 150.0, np.arange(0.0, ts + 0.5, 1.0))
+                eng.simulate(simc, [pt], _lib.make_run(nsims=1000, seed=SEED), want=("mean",))
+                best = None
+                for rep in range(3):
+                    t1 = time.perf_counter()
+                    eng.simulate(simc, [pt], _lib.make_run(nsims=1000, seed=SEED + 1 + rep), want=("mean",))
+                    wall = time.perf_counter() - t1
+                    st = eng.stats()
+                    if best is None or wall < best[0]:
+                        best = (wall, st)
+                small[nm] = {"wall_ms": best[0] * 1e3, "device_ms": best[1]["device_ms"], "events": best[1]["events"],
+                             "events_per_sec": best[1]["events"] / best[0]}
 
     if rank == 0:
         # ---- roofline of the dominant kernel (spr_traj_kernel): SM issue rate and shared-memory bandwidth
         f_mhz = clocks.get("sm_mhz") or 1965.0
         f_hz = f_mhz * 1e6
-        # events-weighted algorithmic shared-memory bytes per event: 4N + c(10 + 11 deg), c = 1.9
-        reach_of = np.array([_lib.load().sprb200_grid_value(RANGES["reach"][0], RANGES["reach"][1],
-                                                            NREACH_PER_GPU * world, int((i - 1) // 1000))
-                             for i in idx])
-        deg = np.array([mean_degree(r, L) for r in reach_of])
-        balg = 4.0 * NPART + 1.9 * (10.0 + 11.0 * deg)
-        balg_mean = float((balg * nev_host).sum() / max(nev_host.sum(), 1.0))
+        # events-weighted algorithmic shared-memory bytes per event: 4N + c(10 + 11 deg), c = 1.9;
+        # weights = the a-priori event shares of the reach values (the per-point events stay on the device)
+        pts_np = grid_points_np(RANGES, size4)
+        ev_np, deg_np = apriori_events(pts_np)
+        balg = 4.0 * NPART + 1.9 * (10.0 + 11.0 * deg_np)
+        balg_mean = float((balg * ev_np).sum() / ev_np.sum())
         ev_rate_kernel = ev_total / world / (traj_ms_total * 1e-3)         # per GPU, trajectory kernel (K1) time only
         smem_peak = SMEM_B_PER_CLK * f_hz / 1e9
         smem_ach = ev_rate_kernel * balg_mean / 1e9
         issue_peak = ISSUE_PER_CLK * f_hz
+        prof = measured_profile()
         roofline = {
             "bound": "smem", "kernel": "spr_traj_kernel", "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s",
-            "frac": smem_ach / smem_peak, "traffic": None,
+            "frac": smem_ach / smem_peak,
+            "traffic": (prof or {}).get("dram_bytes_per_launch"),
             "note": "path is neither HBM- nor tensor-bound (SURVEY.md 8d): achieved = events/s/GPU x flat-scan "
                     "algorithmic shared-memory bytes per event (%.0f B, events-weighted 4N + 1.9(10+11deg)); peak = "
                     "148 SM x 128 B/clk x measured SM clock %.0f MHz (fallback formula of SURVEY.md 8d, not in "
                     "MEASURED_PEAKS.json); kernel time = CUDA events around the K1 launches on the library's stream, "
-                    "live in this run" % (balg_mean, f_mhz),
+                    "live in this run; traffic = dram bytes read+written by one K1 launch of the ncu capture in "
+                    "`measured`" % (balg_mean, f_mhz),
             "events_per_sec_per_gpu_kernel": ev_rate_kernel,
-            "kernel_ms_per_step": {"spr_traj_kernel": traj_ms_total / K, "spr_table_kernel": table_ms_total / K,
-                                   "build_total": build_ms_total / K},
+            "kernel_ms_per_step": {"spr_traj_kernel": traj_ms_total / K, "spr_traj_kernel_fastest_rank": traj_ms_min / K,
+                                   "spr_table_kernel": table_ms_total / K, "build_total": build_ms_total / K},
+            "measured": prof,
         }
         roofline_issue = {
             "bound": "issue", "achieved": ev_rate_kernel * I_ALG, "peak": issue_peak, "unit": "warp-inst/s",
             "frac": ev_rate_kernel * I_ALG / issue_peak,
-            "note": "flat-scan algorithmic warp-instructions per event I_alg = %.0f (SURVEY.md 8d); executed: 202-224 "
-                    "warp-instructions per event, 56-65 %% of issue slots active (ncu sm__inst_executed / "
-                    "smsp__issue_active, profiles/r1_ncu_full_c2_class*.txt)" % I_ALG,
+            "note": "flat-scan algorithmic warp-instructions per event I_alg = %.0f (SURVEY.md 8d); what the kernel "
+                    "really executes per event and the issue-slot utilisation ncu measures are in roofline.measured" % I_ALG,
         }
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -367,22 +495,40 @@ def main():
             "dtype": "f64 clock / int32 counts", "data": "synthetic", "config": config(world),
             "trajectories_per_sec": traj_total / (ms_total * 1e-3),
             "events_per_step": ev_total / K, "build_wall_s": ms_total / K * 1e-3,
-            "clocks": clocks, "gpu_launches": launches_total,
+            "clocks": clocks, "gpu_launches": int(launches_total),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": E2E_STEPS},
+                    "steps": K},
             "roofline": roofline, "roofline_issue": roofline_issue,
         }
+        if strong is not None:
+            out["strong"] = strong
+            out["small_batch"] = small
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import ref_oracle as R
-            R.build()
-            r = run_cpu_reference(ncores, 4242)
+            cpu = CpuPort()
+            pts = grid_points_np(RANGES, NK + (NREACH_PER_GPU,))
+            evp, degp = apriori_events(pts)
+            r = cpu.rate(pts, evp, degp, 777, 4242)
             out["cpu_baseline"] = {
-                "value": r["events"] / r["seconds"], "unit": UNIT, "cores": ncores, "kind": "port",
-                "trajectories_per_sec": r["trajectories"] / r["seconds"], "seconds": r["seconds"],
-                "sample": "%d of the 10^4 C2 grid points (seeded uniform subset) x %d replicates; oracle/spr_ref.c = "
-                          "restatement of the reference algorithm (heap next-reaction SSA, O(N^2) setup per replicate), "
-                          "one thread per host core" % (r["points"], NREP)}
+                "value": r["value"], "unit": UNIT, "cores": cpu.ncores, "kind": "port",
+                "projected_c2_build_seconds": r["wall_projected"], "sample_seconds": r["sample_wall"],
+                "sample": sample_text(r, "10^4 C2 grid")}
+            if c3 is not None:
+                # the same lattice on the CPU port with the same terminator, stratified sample, same run
+                pts3 = grid_points_np(C3_RANGES, C3_LATTICE)
+                ev3, deg3 = apriori_events(pts3)
+                r3 = cpu.rate(pts3, ev3, deg3, 778, 4343, term=C3_TERM, budget_core_s=20.0 * ncores)
+                PF, P3 = int(np.prod(C3_SIZE)), int(np.prod(C3_LATTICE))
+                c3.update({
+                    "cpu_cores": cpu.ncores, "cpu_projected_full_build_s": r3["wall_projected"] * PF / P3,
+                    "cpu_projected_full_build_core_hours": r3["core_seconds_total"] * PF / P3 / 3600.0,
+                    "cpu_sample_seconds": r3["sample_wall"], "cpu_events_per_sec": r3["value"],
+                    "cpu_sample": sample_text(r3, "14,000 lattice"),
+                    "speedup_projected": r3["wall_projected"] / (strong["strong_ms"] * 1e-3),
+                    "reference_documented_cpu_hours": "500-2000 (docs/src/surrogate_construction.md:121-123)"})
+        if c3 is not None:
+            out["c3_sample"] = c3
         print(json.dumps(out))
+    eng.comm_destroy()
     if world > 1:
         dist.destroy_process_group()
     eng.close()

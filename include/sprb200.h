@@ -25,10 +25,13 @@
  *   src/parameters.jl:124-150, src/utils.jl:10               |
  * surrogate_sprdata_error(optpars, pars)                      | sprb200_surrogate_load,
  *   src/fitting.jl:38-91 (5-D interpolation + l2 loss)       | sprb200_fit_loss (whole population)
- * (none: the reference is single-process)                    | sprb200_build_slice_device,
- *                                                            | sprb200_scatter_table_device:
- *                                                            | device-resident slabs for the
- *                                                            | one-rank-per-GPU NCCL gather
+ * the index-range split over independent processes         | sprb200_build_table_multi (all GPUs
+ *   examples/cluster_scripts/queue_job.sh:7-17 +             |   of one process), sprb200_comm_* +
+ *   merge_surrogate_slices src/surrogate.jl:302-332          |   sprb200_build_table_dist (one
+ *                                                            |   process per GPU, NCCL gather),
+ *                                                            | sprb200_deal_indices; device-resident
+ *                                                            | slabs: sprb200_build_slice_device,
+ *                                                            | sprb200_scatter_table_device
  */
 #ifndef SPRB200_H
 #define SPRB200_H
@@ -39,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SPRB200_ABI_VERSION 1
+#define SPRB200_ABI_VERSION 2
 
 /* error codes (all negative); 0 = success */
 enum {
@@ -49,7 +52,8 @@ enum {
     SPRB200_ERR_CUDA = -3,         /* CUDA runtime error, text in sprb200_last_error */
     SPRB200_ERR_TOO_LARGE = -4,    /* per-trajectory state does not fit in shared memory */
     SPRB200_ERR_ALLOC = -5,        /* host or device allocation failed */
-    SPRB200_ERR_INTERNAL = -6
+    SPRB200_ERR_INTERNAL = -6,
+    SPRB200_ERR_NCCL = -7          /* libnccl.so.2 missing or an NCCL call failed (multi-GPU entry points only) */
 };
 
 typedef struct sprb200_ctx *sprb200_handle;
@@ -215,6 +219,44 @@ int sprb200_build_indices(sprb200_handle h, const SprGrid *grid, const SprSim *s
 /* d_table[s*P + idx[k]-1] = d_rows[k*T + s] for a host index list (after the NCCL gather). */
 int sprb200_scatter_rows_device(sprb200_handle h, const double *d_rows, const int64_t *idx,
                                 int64_t count, int32_t T, int64_t P, double *d_table);
+
+/* ---- multi-GPU builds (the reference's "distributed backend" is the split of the linear index range over
+ * independent processes, examples/cluster_scripts/queue_job.sh:7-17, merged afterwards by
+ * merge_surrogate_slices, surrogate.jl:302-332).  Every (point, replicate) trajectory is independent and
+ * its random stream is keyed by (seed, linear index - 1, replicate): the table is byte-identical for
+ * any number of GPUs.  The grid points are dealt to the GPUs in snake order of the a-priori cost estimate
+ * (equal cost mix and equal counts per GPU). ------------------------------------------------------- */
+/* The 1-based linear indices `rank` of `nranks` simulates (ascending).  Device-free.  Writes at most `cap`
+ * indices to idx_out (may be NULL) and returns the count, or a negative error. */
+int64_t sprb200_deal_indices(const SprGrid *grid, const SprSim *sim, int32_t nranks, int32_t rank,
+                             int64_t *idx_out, int64_t cap);
+/* build_surrogate_serial on ndev GPUs of THIS process: one host thread and one context per device (created
+ * on first use, kept until sprb200_multi_release), every device simulates its share, the slabs are
+ * gathered on devices[0] with peer copies (NVLink), permuted there into FirstMoment order and copied
+ * to out_table ((n1,n2,n3,n4,T) column-major, host).  n_used / n_events: [P] host or NULL.
+ * Error text: sprb200_last_error(NULL). */
+int sprb200_build_table_multi(const int32_t *devices, int32_t ndev, const SprGrid *grid, const SprSim *sim,
+                              const SprRun *run, double *out_table, int32_t *n_used, uint64_t *n_events);
+/* Per-device counters of the last sprb200_build_table_multi call: events simulated, device milliseconds of the
+ * whole share and of the trajectory kernel alone (each [ndev] or NULL). */
+int sprb200_multi_stats(const int32_t *devices, int32_t ndev, uint64_t *events, double *device_ms, double *traj_ms);
+/* Destroys the contexts sprb200_build_table_multi created. */
+void sprb200_multi_release(void);
+
+/* One process per GPU (MPI / torchrun / one Julia worker per GPU).  NCCL is bound at run time (dlopen of
+ * libnccl.so.2; SPRB200_ERR_NCCL if absent) and used for exactly one exchange: the all-gather of the
+ * mean-curve slabs.  Rank 0 calls sprb200_comm_unique_id and hands the 128 bytes to every rank by any
+ * means (MPI_Bcast, a file, torch.distributed); every rank then calls sprb200_comm_init (collective). */
+int sprb200_comm_unique_id(unsigned char id_out[128]);
+int sprb200_comm_init(sprb200_handle h, const unsigned char id[128], int32_t nranks, int32_t rank);
+int sprb200_comm_destroy(sprb200_handle h);
+/* build_surrogate_serial across the communicator (collective: every rank calls it with the same arguments).
+ * Each rank simulates its share (sprb200_deal_indices), one ncclAllGather assembles the slabs on every
+ * rank and the table is permuted on the device into FirstMoment order.  out_table (host, P*T doubles) and
+ * d_table (device, P*T doubles) may each be NULL; n_used / n_events: [P] host or NULL.  With nranks == 1
+ * no communicator is needed.  sprb200_last_stats / sprb200_last_kernel_ms report this rank's share. */
+int sprb200_build_table_dist(sprb200_handle h, const SprGrid *grid, const SprSim *sim, const SprRun *run,
+                             double *out_table, double *d_table, int32_t *n_used, uint64_t *n_events);
 
 /* ---- the consumer of the table: surrogate_sprdata_error (src/fitting.jl:38-91) ------------------- */
 /* Mirror of AlignedData (src/spr_data.jl:9-18) in concatenated form. */

@@ -48,6 +48,63 @@ def build(force=False):
         subprocess.check_call(["make", "-C", _HERE, "-B", "all"], stdout=subprocess.DEVNULL)
 
 
+def _bind_timed(L):
+    L.spr_ref_run_points_timed.restype = C.c_int
+    L.spr_ref_run_points_timed.argtypes = [C.POINTER(RefBioPars), C.c_int64, C.POINTER(RefSimPars),
+                                           C.POINTER(RefTerm), C.c_uint64, C.POINTER(C.c_uint64),
+                                           C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_double),
+                                           C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+
+
+def build_native(outdir=None):
+    """The CPU-baseline build of spr_ref.c for bench.py: compiled ON the machine that times it, with
+    -O3 -march=native and floating-point contraction left on (the checker build above pins x86-64-v3 and
+    -ffp-contract=off only because it travels between machines and the mirror needs bit-exact arithmetic).
+    Returns a ctypes handle bound like lib()."""
+    outdir = outdir or os.path.join(_HERE, "_bench")
+    os.makedirs(outdir, exist_ok=True)
+    so = os.path.join(outdir, "libspr_ref_native.so")
+    src = os.path.join(_HERE, "spr_ref.c")
+    subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-std=gnu11", "-shared", "-o", so, src,
+                           "-lm", "-lpthread"])
+    L = C.CDLL(so)
+    _bind_timed(L)
+    return L
+
+
+def run_points_timed(points, sim, term, nsims_per_point=None, seed=1, streams=None, nthreads=None, L=None):
+    """run_points with a replicate count per point and per-point wall seconds (bench.py's CPU legs).
+    Returns (nobs, nevents, seconds, wall)."""
+    import time
+    L = L or lib()
+    nthreads = nthreads or os.cpu_count()
+    points = np.asarray(points, dtype=np.float64)
+    npts = len(points)
+    arr = (RefBioPars * npts)()
+    for k in range(npts):
+        arr[k] = RefBioPars(points[k, 0], points[k, 1], points[k, 2], points[k, 3], 1.0,
+                            DEFAULT_SIM_ANTIGENCONCEN, 1.0)
+    nobs = np.zeros(npts, dtype=np.int64)
+    nev = np.zeros(npts, dtype=np.uint64)
+    secs = np.zeros(npts)
+    st = None
+    if streams is not None:
+        st_arr = np.ascontiguousarray(streams, dtype=np.uint64)
+        st = st_arr.ctypes.data_as(C.POINTER(C.c_uint64))
+    ns = None
+    if nsims_per_point is not None:
+        ns_arr = np.ascontiguousarray(nsims_per_point, dtype=np.int32)
+        ns = ns_arr.ctypes.data_as(C.POINTER(C.c_int32))
+    t0 = time.perf_counter()
+    rc = L.spr_ref_run_points_timed(arr, npts, C.byref(sim.c), C.byref(term), seed, st, ns, nthreads, None,
+                                    nobs.ctypes.data_as(C.POINTER(C.c_int64)),
+                                    nev.ctypes.data_as(C.POINTER(C.c_uint64)), _dp(secs))
+    wall = time.perf_counter() - t0
+    if rc != 0:
+        raise ValueError("spr_ref_run_points_timed failed: %d" % rc)
+    return nobs, nev, secs, wall
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -77,6 +134,7 @@ def lib():
                                          C.POINTER(RefTerm), C.c_uint64, C.POINTER(C.c_uint64), C.c_int,
                                          C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                          C.POINTER(C.c_uint64)]
+        _bind_timed(L)
         L.spr_ref_grid_value.restype = C.c_double
         L.spr_ref_grid_value.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
         _LIB = L

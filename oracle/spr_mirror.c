@@ -394,7 +394,12 @@ int spr_mirror_point(const MirrorSim *sim, double kon_eff, double koff, double k
             sumsq[s] += v * v;
             if (term_kind == 1 && n >= minsims && n < maxsims) {
                 double dS = (double)sum[s];
-                double num = (double)((uint64_t)n * sumsq[s] - (uint64_t)(sum[s] * sum[s]));
+                /* n*Q - S^2 in 128 bits, converted as hi * 2^64 + lo */
+                unsigned __int128 d = (unsigned __int128)(uint64_t)n * sumsq[s] -
+                                      (unsigned __int128)(uint64_t)sum[s] * (uint64_t)sum[s];
+                uint64_t hi = (uint64_t)(d >> 64), lo = (uint64_t)d;
+                double num = (double)lo;
+                if (hi) num = (double)hi * 18446744073709551616.0 + num;
                 if (num > tol2 * dS * dS * (double)(n - 1)) viol = 1;
             }
         }

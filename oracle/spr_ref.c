@@ -35,6 +35,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 /* ------------------------------------------------------------------ RNG (oracle-private) */
 typedef struct { uint64_t s[4]; } rng_t;
@@ -581,6 +582,54 @@ int spr_ref_run_points(const RefBioPars *pts, int64_t npts, const RefSimPars *si
     if (nthreads > 1024) nthreads = 1024;
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
     for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, points_worker, &job);
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(th);
+    return 0;
+}
+
+/* the same sweep with a replicate count per point and the wall seconds each point took on its thread while
+ * all other threads were busy (bench.py: stratified, bounded sample of a grid; FIXED terminator only when
+ * nsims_per_point is given) */
+typedef struct {
+    points_job_t base;
+    const int32_t *nsims;
+    double *seconds;
+} timed_job_t;
+
+static void *timed_worker(void *arg) {
+    timed_job_t *tj = (timed_job_t *)arg;
+    points_job_t *job = &tj->base;
+    for (;;) {
+        long long k = atomic_fetch_add(&job->next, 1);
+        if (k >= job->npts) break;
+        RefSimPars sim = *job->sim;
+        if (tj->nsims) sim.nsims = tj->nsims[k];
+        struct timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        uint64_t nev = 0;
+        int64_t n = spr_ref_run(&job->pts[k], &sim, job->term, job->seed,
+                                job->streams ? job->streams[k] : (uint64_t)k, 0,
+                                job->out ? job->out + (size_t)k * sim.T : NULL, NULL, &nev, NULL, 0);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        if (job->nobs) job->nobs[k] = n;
+        if (job->nevents) job->nevents[k] = nev;
+        if (tj->seconds) tj->seconds[k] = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    }
+    return NULL;
+}
+
+int spr_ref_run_points_timed(const RefBioPars *pts, int64_t npts, const RefSimPars *sim, const RefTerm *term,
+                             uint64_t seed, const uint64_t *streams, const int32_t *nsims_per_point, int nthreads,
+                             double *out_TxNpts, int64_t *nobs, uint64_t *nevents, double *seconds) {
+    timed_job_t tj;
+    tj.base.pts = pts; tj.base.sim = sim; tj.base.term = term; tj.base.npts = npts; tj.base.seed = seed;
+    tj.base.streams = streams; tj.base.out = out_TxNpts; tj.base.nobs = nobs; tj.base.nevents = nevents;
+    tj.nsims = nsims_per_point; tj.seconds = seconds;
+    atomic_init(&tj.base.next, 0);
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 1024) nthreads = 1024;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+    for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, timed_worker, &tj);
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
     free(th);
     return 0;

@@ -11,7 +11,7 @@ LIB = os.path.join(LIBDIR, "libsprb200.so")
 SOURCES = ["spr_kernels.cu", "spr_api.cu"]
 HEADERS = ["spr_device.cuh", "spr_kernels.cuh", os.path.join("..", "..", "include", "sprb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O2,-Wall", "--fmad=false", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC,-O2,-Wall,-pthread", "--fmad=false", "-Xptxas", "-v"]
 
 
 def stale():
@@ -27,7 +27,7 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES] + ["-lcudart"]
+    cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES] + ["-lcudart", "-ldl", "-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

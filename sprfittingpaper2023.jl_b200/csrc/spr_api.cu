@@ -11,8 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace spr;
@@ -60,7 +63,11 @@ struct sprb200_ctx {
     std::string err;
     // arenas
     DevBuf tsave, pts, pidx, order, curve, curve2, sum, sumsq, nused, nevents, nscanned, nstar, active, counters,
-        rows, locs, goff, gnbr, misc, table, arena, desc, defer, tickets, slotrec, stage, sur, fitdata, fitpars, fitloss;
+        rows, locs, goff, gnbr, misc, table, arena, desc, defer, tickets, slotrec, stage, sur, fitdata, fitpars, fitloss,
+        mrows, mtable, midx, mnused, mnev, gnused, gnev;
+    // multi-GPU (sprb200_comm_init): NCCL communicator of this rank, dlopen'ed libnccl
+    void *nccl_comm = nullptr;
+    int comm_rank = 0, comm_nranks = 1;
     // stats of the last call
     uint64_t st_traj = 0, st_events = 0, st_launches = 0;
     double st_ms = 0.0, st_table_ms = 0.0, st_traj_ms = 0.0;
@@ -115,6 +122,8 @@ int check_sim(sprb200_ctx *h, const SprSim *sim) {
         if (s && sim->tsave[s] < sim->tsave[s - 1]) return fail(h, SPRB200_ERR_BAD_ARG, "tsave must be ascending");
     }
     if (std::isnan(sim->tstop) || std::isnan(sim->tstop_AtoB)) return fail(h, SPRB200_ERR_BAD_ARG, "tstop/tstop_AtoB is NaN");
+    // an infinite tstop with positive rates never ends (the reference's tsave = 0:dt:tstop needs a finite one too)
+    if (!std::isfinite(sim->tstop)) return fail(h, SPRB200_ERR_BAD_ARG, "tstop must be finite");
     if (!sim->resample_initlocs && !sim->initlocs)
         return fail(h, SPRB200_ERR_BAD_ARG, "initlocs required when resample_initlocs == 0");
     return SPRB200_OK;
@@ -487,7 +496,10 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                         lay.cta_per_sm = std::max(1, h->max_warps / lay.wpc);
                     }
                     TrajArgs a{};
-                    a.N = N; a.T = T; a.tstop = sim->tstop; a.toff = sim->tstop_AtoB;
+                    a.N = N; a.T = T; a.tstop = sim->tstop;
+                    // tstop_AtoB <= 0: the bath is off from t = 0 on; the clock must not move backwards
+                    // (the reference keeps tc = 0 and only zeroes kon, forward_simulator.jl:174-181)
+                    a.toff = std::max(sim->tstop_AtoB, 0.0);
                     a.tsave = h->tsave.as<double>();
                     a.pts = h->pts.as<PointDev>(); a.pidx = h->pidx.as<uint32_t>(); a.order = h->order.as<int32_t>();
                     a.tk0 = tk0; a.ntickets = n;
@@ -641,6 +653,82 @@ std::vector<int64_t> strided(int64_t idxstart, int64_t stride, int64_t count) {
     return v;
 }
 
+
+// ---- cost-balanced deal of grid points to ranks (multi-GPU builds) ------------------------------
+// The points, sorted by the a-priori cost estimate (descending, ties by index), are handed out in snake
+// order 0..w-1, w-1..0, ...: every rank simulates the same mix of cheap and expensive points and the
+// counts differ by at most one.  Deterministic and device-free: every rank computes the same lists.
+// The reference's own split is by contiguous index ranges (examples/cluster_scripts/queue_job.sh:7-17).
+int deal_points(const SprGrid *grid, const SprSim *sim, int nranks, std::vector<std::vector<int64_t>> *out) {
+    int64_t P = 0;
+    if (grid_total(grid, &P) || nranks < 1) return SPRB200_ERR_BAD_ARG;
+    std::vector<std::pair<double, int64_t>> keyed((size_t)P);
+    for (int64_t i = 0; i < P; ++i) {
+        PointDev p;
+        grid_point(grid, i, &p);
+        keyed[(size_t)i] = std::make_pair(-cost_estimate(p, sim->N, sim->DIM, sim->L, sim->tstop, sim->tstop_AtoB), i);
+    }
+    std::sort(keyed.begin(), keyed.end());
+    out->assign((size_t)nranks, std::vector<int64_t>());
+    for (auto &v : *out) v.reserve((size_t)(P / nranks + 1));
+    for (int64_t k = 0; k < P; ++k) {
+        const int64_t lap = k / nranks, within = k % nranks;
+        const int r = (int)((lap & 1) ? nranks - 1 - within : within);
+        (*out)[(size_t)r].push_back(keyed[(size_t)k].second + 1);   // 1-based linear index
+    }
+    for (auto &v : *out) std::sort(v.begin(), v.end());
+    return SPRB200_OK;
+}
+
+// ---- NCCL, bound at run time (dlopen): the library has no link-time dependency on it, a single-GPU
+// caller never needs it, and inside a process that already loaded NCCL (PyTorch) the same copy is used.
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId /* ncclUniqueId, by value */, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mutex;
+
+bool nccl_load(std::string *err) {
+    std::lock_guard<std::mutex> lk(g_nccl_mutex);
+    if (g_nccl.lib) return true;
+    const char *names[] = {std::getenv("SPRB200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *lib = nullptr;
+    for (const char *nm : names) {
+        if (!nm || !*nm) continue;
+        lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) { *err = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found"); return false; }
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+    g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(lib, "ncclAllGather"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather) {
+        *err = "libnccl.so.2 lacks ncclGetUniqueId/ncclCommInitRank/ncclCommDestroy/ncclAllGather";
+        dlclose(lib);
+        return false;
+    }
+    g_nccl.lib = lib;
+    return true;
+}
+#define NCCL_TRY(h, expr)                                                                         \
+    do {                                                                                          \
+        int r__ = (expr);                                                                         \
+        if (r__ != 0)                                                                             \
+            return fail(h, SPRB200_ERR_NCCL, std::string(#expr) + ": " +                          \
+                                                 (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "NCCL error")); \
+    } while (0)
+
+// handles owned by sprb200_build_table_multi (one per device, kept for the life of the process)
+std::map<int, sprb200_ctx *> g_multi_handles;
+std::mutex g_multi_mutex;
 }  // namespace
 
 // ================================================================================================
@@ -702,9 +790,14 @@ void sprb200_destroy(sprb200_handle h) {
     for (int s = 0; s < NSTREAM; ++s) {
         if (h->stream[s]) cudaStreamSynchronize(h->stream[s]);
     }
+    if (h->nccl_comm && g_nccl.CommDestroy) {
+        g_nccl.CommDestroy(h->nccl_comm);
+        h->nccl_comm = nullptr;
+    }
     DevBuf *bufs[] = {&h->tsave, &h->pts, &h->pidx, &h->order, &h->curve, &h->curve2, &h->sum, &h->sumsq, &h->nused,
                       &h->nevents, &h->nscanned, &h->nstar, &h->active, &h->counters, &h->rows, &h->locs,
-                      &h->goff, &h->gnbr, &h->misc, &h->table, &h->arena, &h->desc, &h->defer, &h->tickets, &h->slotrec, &h->stage, &h->sur, &h->fitdata, &h->fitpars, &h->fitloss};
+                      &h->goff, &h->gnbr, &h->misc, &h->table, &h->arena, &h->desc, &h->defer, &h->tickets, &h->slotrec, &h->stage, &h->sur, &h->fitdata, &h->fitpars, &h->fitloss,
+                      &h->mrows, &h->mtable, &h->midx, &h->mnused, &h->mnev, &h->gnused, &h->gnev};
     for (DevBuf *b : bufs) b->release();
     for (int s = 0; s < NSTREAM; ++s) {
         if (h->stream[s]) cudaStreamDestroy(h->stream[s]);
@@ -1103,6 +1196,265 @@ int sprb200_scatter_table_device(sprb200_handle h, const double *d_rows, int64_t
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, launch_scatter(d_rows, idxstart - 1, stride, count, T, P, d_table, h->stream[0]));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream[0]));
+    return SPRB200_OK;
+}
+
+// ---- multi-GPU -------------------------------------------------------------------------------------
+int64_t sprb200_deal_indices(const SprGrid *grid, const SprSim *sim, int32_t nranks, int32_t rank, int64_t *idx_out,
+                             int64_t cap) {
+    if (!grid || !sim || nranks < 1 || rank < 0 || rank >= nranks || sim->N < 1 || (sim->DIM != 2 && sim->DIM != 3) ||
+        !(sim->L > 0.0))
+        return SPRB200_ERR_BAD_ARG;
+    std::vector<std::vector<int64_t>> deal;
+    if (deal_points(grid, sim, nranks, &deal)) return SPRB200_ERR_BAD_ARG;
+    const std::vector<int64_t> &mine = deal[(size_t)rank];
+    if (idx_out)
+        for (size_t k = 0; k < mine.size() && (int64_t)k < cap; ++k) idx_out[k] = mine[k];
+    return (int64_t)mine.size();
+}
+
+int sprb200_build_table_multi(const int32_t *devices, int32_t ndev, const SprGrid *grid, const SprSim *sim,
+                              const SprRun *run, double *out_table, int32_t *n_used, uint64_t *n_events) {
+    if (!devices || ndev < 1 || ndev > 64) return fail(nullptr, SPRB200_ERR_BAD_ARG, "need 1..64 devices");
+    int64_t P = 0;
+    if (grid_total(grid, &P)) return fail(nullptr, SPRB200_ERR_BAD_ARG, "bad grid");
+    if (!out_table || !sim || sim->T < 1) return fail(nullptr, SPRB200_ERR_BAD_ARG, "bad table arguments");
+    for (int a = 0; a < ndev; ++a)
+        for (int b = a + 1; b < ndev; ++b)
+            if (devices[a] == devices[b]) return fail(nullptr, SPRB200_ERR_BAD_ARG, "device listed twice");
+    std::lock_guard<std::mutex> lk(g_multi_mutex);     // one multi-GPU build at a time per process
+    std::vector<sprb200_ctx *> hs((size_t)ndev, nullptr);
+    for (int r = 0; r < ndev; ++r) {
+        auto it = g_multi_handles.find(devices[r]);
+        if (it == g_multi_handles.end()) {
+            sprb200_handle nh = nullptr;
+            const int rc = sprb200_create(devices[r], &nh);
+            if (rc) return rc;      // text is in the thread-local create error
+            it = g_multi_handles.emplace(devices[r], nh).first;
+        }
+        hs[(size_t)r] = it->second;
+    }
+    std::vector<std::vector<int64_t>> deal;
+    if (deal_points(grid, sim, ndev, &deal)) return fail(nullptr, SPRB200_ERR_BAD_ARG, "bad grid");
+    const int T = sim->T;
+    sprb200_ctx *h0 = hs[0];
+    // the gathered slabs and the table live on the first device; every other device sends its slab with
+    // one peer copy (NVLink when peer access is available, staged by the driver otherwise)
+    if (cudaSetDevice(h0->device) != cudaSuccess) return fail(nullptr, SPRB200_ERR_CUDA, "cudaSetDevice");
+    const size_t elems = (size_t)P * (size_t)T;
+    {
+        cudaError_t e = h0->mrows.ensure(sizeof(double) * elems);
+        if (e == cudaSuccess) e = h0->mtable.ensure(sizeof(double) * elems);
+        if (e == cudaSuccess) e = h0->midx.ensure(sizeof(int64_t) * (size_t)P);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SPRB200_ERR_ALLOC, "device memory for the gathered table"); }
+    }
+    for (int r = 1; r < ndev; ++r) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, h0->device, hs[(size_t)r]->device) == cudaSuccess && can) {
+            cudaDeviceEnablePeerAccess(hs[(size_t)r]->device, 0);
+            cudaGetLastError();     // already enabled is fine
+        }
+    }
+    std::vector<int64_t> offs((size_t)ndev + 1, 0);
+    for (int r = 0; r < ndev; ++r) offs[(size_t)r + 1] = offs[(size_t)r] + (int64_t)deal[(size_t)r].size();
+    std::vector<int> rcs((size_t)ndev, SPRB200_OK);
+    std::vector<std::vector<int32_t>> nus((size_t)ndev);
+    std::vector<std::vector<uint64_t>> nevs((size_t)ndev);
+    auto worker = [&](int r) {
+        sprb200_ctx *h = hs[(size_t)r];
+        const std::vector<int64_t> &idx = deal[(size_t)r];
+        const int64_t count = (int64_t)idx.size();
+        if (count == 0) return;
+        auto body = [&]() -> int {
+            CUDA_TRY(h, cudaSetDevice(h->device));
+            CUDA_TRY(h, h->table.ensure(sizeof(double) * (size_t)count * T));
+            nus[(size_t)r].assign((size_t)count, 0);
+            nevs[(size_t)r].assign((size_t)count, 0);
+            int rc = build_rows(h, grid, sim, run, idx.data(), count, h->table.as<double>(), nullptr, nullptr,
+                                nus[(size_t)r].data(), nevs[(size_t)r].data());
+            if (rc) return rc;
+            CUDA_TRY(h, cudaMemcpyPeerAsync(h0->mrows.as<double>() + (size_t)offs[(size_t)r] * T, h0->device, h->table.p,
+                                            h->device, sizeof(double) * (size_t)count * T, h->stream[0]));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream[0]));
+            return SPRB200_OK;
+        };
+        rcs[(size_t)r] = body();
+    };
+    {
+        std::vector<std::thread> th;
+        for (int r = 1; r < ndev; ++r) th.emplace_back(worker, r);
+        worker(0);
+        for (auto &t : th) t.join();
+    }
+    for (int r = 0; r < ndev; ++r)
+        if (rcs[(size_t)r]) return fail(nullptr, rcs[(size_t)r], "device " + std::to_string(devices[r]) + ": " + hs[(size_t)r]->err);
+    // slabs -> FirstMoment order on the first device, one copy to the caller's table
+    std::vector<int64_t> idx_all;
+    idx_all.reserve((size_t)P);
+    for (int r = 0; r < ndev; ++r) idx_all.insert(idx_all.end(), deal[(size_t)r].begin(), deal[(size_t)r].end());
+    auto tail = [&]() -> int {
+        sprb200_ctx *h = h0;
+        cudaStream_t s0 = h->stream[0];
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        CUDA_TRY(h, cudaMemcpyAsync(h->midx.p, idx_all.data(), sizeof(int64_t) * (size_t)P, cudaMemcpyHostToDevice, s0));
+        CUDA_TRY(h, launch_scatter_idx(h->mrows.as<double>(), h->midx.as<long long>(), P, T, P, h->mtable.as<double>(), s0));
+        h->st_launches += 1;
+        CUDA_TRY(h, cudaMemcpyAsync(out_table, h->mtable.p, sizeof(double) * elems, cudaMemcpyDeviceToHost, s0));
+        CUDA_TRY(h, cudaStreamSynchronize(s0));
+        return SPRB200_OK;
+    };
+    const int rc = tail();
+    if (rc) return fail(nullptr, rc, h0->err);
+    for (int r = 0; r < ndev; ++r)
+        for (size_t k = 0; k < deal[(size_t)r].size(); ++k) {
+            const int64_t i0 = deal[(size_t)r][k] - 1;
+            if (n_used) n_used[i0] = nus[(size_t)r][k];
+            if (n_events) n_events[i0] = nevs[(size_t)r][k];
+        }
+    return SPRB200_OK;
+}
+
+int sprb200_multi_stats(const int32_t *devices, int32_t ndev, uint64_t *events, double *device_ms, double *traj_ms) {
+    if (!devices || ndev < 1) return SPRB200_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(g_multi_mutex);
+    for (int r = 0; r < ndev; ++r) {
+        auto it = g_multi_handles.find(devices[r]);
+        if (it == g_multi_handles.end()) return SPRB200_ERR_BAD_ARG;
+        if (events) events[r] = it->second->st_events;
+        if (device_ms) device_ms[r] = it->second->st_ms;
+        if (traj_ms) traj_ms[r] = it->second->st_traj_ms;
+    }
+    return SPRB200_OK;
+}
+
+void sprb200_multi_release(void) {
+    std::lock_guard<std::mutex> lk(g_multi_mutex);
+    for (auto &kv : g_multi_handles) sprb200_destroy(kv.second);
+    g_multi_handles.clear();
+}
+
+int sprb200_comm_unique_id(unsigned char id_out[128]) {
+    if (!id_out) return fail(nullptr, SPRB200_ERR_BAD_ARG, "id_out is NULL");
+    std::string err;
+    if (!nccl_load(&err)) return fail(nullptr, SPRB200_ERR_NCCL, err);
+    NcclId id;
+    const int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) return fail(nullptr, SPRB200_ERR_NCCL, std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    std::memcpy(id_out, id.internal, 128);
+    return SPRB200_OK;
+}
+
+int sprb200_comm_init(sprb200_handle h, const unsigned char id[128], int32_t nranks, int32_t rank) {
+    if (!h) return SPRB200_ERR_BAD_ARG;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, SPRB200_ERR_BAD_ARG, "bad rank / nranks");
+    if (h->nccl_comm) return fail(h, SPRB200_ERR_BAD_ARG, "this handle already has a communicator");
+    h->comm_rank = rank;
+    h->comm_nranks = nranks;
+    if (nranks == 1) return SPRB200_OK;       // nothing to exchange
+    if (!id) return fail(h, SPRB200_ERR_BAD_ARG, "id is NULL");
+    std::string err;
+    if (!nccl_load(&err)) return fail(h, SPRB200_ERR_NCCL, err);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    NcclId nid;
+    std::memcpy(nid.internal, id, 128);
+    NCCL_TRY(h, g_nccl.CommInitRank(&h->nccl_comm, nranks, nid, rank));
+    return SPRB200_OK;
+}
+
+int sprb200_comm_destroy(sprb200_handle h) {
+    if (!h) return SPRB200_ERR_BAD_ARG;
+    if (h->nccl_comm) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream[0]);
+        g_nccl.CommDestroy(h->nccl_comm);
+        h->nccl_comm = nullptr;
+    }
+    h->comm_rank = 0;
+    h->comm_nranks = 1;
+    return SPRB200_OK;
+}
+
+int sprb200_build_table_dist(sprb200_handle h, const SprGrid *grid, const SprSim *sim, const SprRun *run,
+                             double *out_table, double *d_table, int32_t *n_used, uint64_t *n_events) {
+    if (!h) return SPRB200_ERR_BAD_ARG;
+    int64_t P = 0;
+    if (grid_total(grid, &P)) return fail(h, SPRB200_ERR_BAD_ARG, "bad grid");
+    if (!sim || sim->T < 1) return fail(h, SPRB200_ERR_BAD_ARG, "sim is NULL");
+    const int nr = h->comm_nranks, me = h->comm_rank;
+    if (nr > 1 && !h->nccl_comm) return fail(h, SPRB200_ERR_BAD_ARG, "no communicator (sprb200_comm_init)");
+    if (P < nr) return fail(h, SPRB200_ERR_BAD_ARG, "fewer grid points than ranks");
+    std::vector<std::vector<int64_t>> deal;
+    if (deal_points(grid, sim, nr, &deal)) return fail(h, SPRB200_ERR_BAD_ARG, "bad grid");
+    const int T = sim->T;
+    const std::vector<int64_t> &mine = deal[(size_t)me];
+    const int64_t count = (int64_t)mine.size();
+    int64_t maxcount = 0;
+    for (auto &v : deal) maxcount = std::max<int64_t>(maxcount, (int64_t)v.size());
+    cudaStream_t s0 = h->stream[0];
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    // this rank's slab [maxcount][T] (rows past `count` are padding), its replicate and event counts
+    CUDA_TRY(h, h->table.ensure(sizeof(double) * (size_t)maxcount * T));
+    CUDA_TRY(h, h->mnused.ensure(sizeof(int32_t) * (size_t)maxcount));
+    CUDA_TRY(h, h->mnev.ensure(sizeof(uint64_t) * (size_t)maxcount));
+    if (count < maxcount) {
+        CUDA_TRY(h, cudaMemsetAsync(h->table.as<double>() + (size_t)count * T, 0, sizeof(double) * (size_t)(maxcount - count) * T, s0));
+        CUDA_TRY(h, cudaMemsetAsync(h->mnused.as<int32_t>() + count, 0, sizeof(int32_t) * (size_t)(maxcount - count), s0));
+        CUDA_TRY(h, cudaMemsetAsync(h->mnev.as<uint64_t>() + count, 0, sizeof(uint64_t) * (size_t)(maxcount - count), s0));
+    }
+    int rc = build_rows(h, grid, sim, run, mine.data(), count, h->table.as<double>(), h->mnused.as<int32_t>(),
+                        h->mnev.as<uint64_t>(), nullptr, nullptr);
+    if (rc) return rc;
+    // run_points keeps its own statistics; the gather below is part of the same call
+    const double *d_rows_all = h->table.as<double>();
+    const int32_t *d_nu_all = h->mnused.as<int32_t>();
+    const uint64_t *d_nev_all = h->mnev.as<uint64_t>();
+    if (nr > 1) {
+        CUDA_TRY(h, h->mrows.ensure(sizeof(double) * (size_t)maxcount * T * nr));
+        NCCL_TRY(h, g_nccl.AllGather(h->table.p, h->mrows.p, sizeof(double) * (size_t)maxcount * T, 0 /* ncclInt8 */,
+                                     h->nccl_comm, s0));
+        d_rows_all = h->mrows.as<double>();
+        if (n_used) {
+            CUDA_TRY(h, h->gnused.ensure(sizeof(int32_t) * (size_t)maxcount * nr));
+            NCCL_TRY(h, g_nccl.AllGather(h->mnused.p, h->gnused.p, sizeof(int32_t) * (size_t)maxcount, 0, h->nccl_comm, s0));
+            d_nu_all = h->gnused.as<int32_t>();
+        }
+        if (n_events) {
+            CUDA_TRY(h, h->gnev.ensure(sizeof(uint64_t) * (size_t)maxcount * nr));
+            NCCL_TRY(h, g_nccl.AllGather(h->mnev.p, h->gnev.p, sizeof(uint64_t) * (size_t)maxcount, 0, h->nccl_comm, s0));
+            d_nev_all = h->gnev.as<uint64_t>();
+        }
+        h->st_launches += 1;
+    }
+    // gathered rows -> FirstMoment order (padding rows carry index 0 and are skipped)
+    std::vector<int64_t> idx_all((size_t)maxcount * nr, 0);
+    for (int r = 0; r < nr; ++r)
+        for (size_t k = 0; k < deal[(size_t)r].size(); ++k) idx_all[(size_t)r * maxcount + k] = deal[(size_t)r][k];
+    CUDA_TRY(h, h->midx.ensure(sizeof(int64_t) * idx_all.size()));
+    CUDA_TRY(h, cudaMemcpyAsync(h->midx.p, idx_all.data(), sizeof(int64_t) * idx_all.size(), cudaMemcpyHostToDevice, s0));
+    double *d_out = d_table;
+    if (!d_out) {
+        CUDA_TRY(h, h->mtable.ensure(sizeof(double) * (size_t)P * T));
+        d_out = h->mtable.as<double>();
+    }
+    CUDA_TRY(h, launch_scatter_idx(d_rows_all, h->midx.as<long long>(), (long long)idx_all.size(), T, P, d_out, s0));
+    h->st_launches += 1;
+    if (out_table) CUDA_TRY(h, cudaMemcpyAsync(out_table, d_out, sizeof(double) * (size_t)P * T, cudaMemcpyDeviceToHost, s0));
+    std::vector<int32_t> nu_h;
+    std::vector<uint64_t> nev_h;
+    if (n_used) {
+        nu_h.resize(idx_all.size());
+        CUDA_TRY(h, cudaMemcpyAsync(nu_h.data(), d_nu_all, sizeof(int32_t) * idx_all.size(), cudaMemcpyDeviceToHost, s0));
+    }
+    if (n_events) {
+        nev_h.resize(idx_all.size());
+        CUDA_TRY(h, cudaMemcpyAsync(nev_h.data(), d_nev_all, sizeof(uint64_t) * idx_all.size(), cudaMemcpyDeviceToHost, s0));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(s0));
+    for (size_t k = 0; k < idx_all.size(); ++k) {
+        if (idx_all[k] < 1) continue;
+        if (n_used) n_used[idx_all[k] - 1] = nu_h[k];
+        if (n_events) n_events[idx_all[k] - 1] = nev_h[k];
+    }
     return SPRB200_OK;
 }
 

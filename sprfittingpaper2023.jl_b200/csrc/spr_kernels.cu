@@ -800,6 +800,18 @@ __global__ void reduce_fixed_kernel(const uint16_t *__restrict__ curve, int reps
     }
 }
 
+// n*Q - S^2 (>= 0 by Cauchy-Schwarz) as a double.  The product n*Q passes 2^64 once n*N exceeds about 3e9
+// (maxsims up to 10^6 with N up to 65535), so the difference is formed in 128 bits; it is converted as
+// hi * 2^64 + lo with explicit roundings, the sequence oracle/spr_mirror.c repeats (hi == 0 in every
+// realistic configuration: then this is the plain conversion of a 64-bit integer).
+__device__ __forceinline__ double var_numerator(unsigned long long n, unsigned long long Q, unsigned long long S) {
+    const unsigned __int128 d = (unsigned __int128)n * Q - (unsigned __int128)S * S;
+    const unsigned long long hi = (unsigned long long)(d >> 64), lo = (unsigned long long)d;
+    const double dlo = __ull2double_rn(lo);
+    if (hi == 0ULL) return dlo;
+    return __dadd_rn(__dmul_rn(__ull2double_rn(hi), 18446744073709551616.0), dlo);
+}
+
 // K3 (VarianceTerminator): continue the sequential scan of replicates nscanned+1 .. navail of every
 // active slot; nstar = first n >= minsims with std <= ssetol*mean*sqrt(n) in every bin, or maxsims
 // (callbacks.jl:204-217).  With integer moments S = sum x, Q = sum x^2 the bin test
@@ -827,8 +839,7 @@ __global__ void variance_scan_kernel(const uint16_t *__restrict__ curve, const i
             sumsq[(size_t)slot * T + s] = Q;
             if (n >= minsims && n < maxsims) {
                 const double dS = (double)S;
-                const double num = (double)((unsigned long long)n * Q - (unsigned long long)(S * S));
-                if (num > tol2 * dS * dS * (double)(n - 1)) viol = 1;
+                if (var_numerator((unsigned long long)n, Q, (unsigned long long)S) > tol2 * dS * dS * (double)(n - 1)) viol = 1;
             }
         }
         if (n < minsims) continue;                 // uniform across the block
@@ -884,7 +895,10 @@ __global__ void scatter_idx_kernel(const double *__restrict__ rows, const long l
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int s = s0 + r;
         const long long k = k0 + threadIdx.x;
-        if (k < count && s < T) table[(size_t)s * P + (size_t)(idx1[k] - 1)] = tile[threadIdx.x][r];
+        if (k < count && s < T) {
+            const long long i1 = idx1[k];       // < 1: padding row of a gathered slab, no table column
+            if (i1 >= 1) table[(size_t)s * P + (size_t)(i1 - 1)] = tile[threadIdx.x][r];
+        }
     }
 }
 

@@ -8,9 +8,9 @@ import numpy as np
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("SPRB200_LIB") or os.path.join(_PKG, "lib", "libsprb200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK = 0
-ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_TOO_LARGE, ERR_ALLOC, ERR_INTERNAL = -1, -2, -3, -4, -5, -6
+ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_TOO_LARGE, ERR_ALLOC, ERR_INTERNAL, ERR_NCCL = -1, -2, -3, -4, -5, -6, -7
 TERM_FIXED, TERM_VARIANCE = 0, 1
 OBS_TOTAL_BOUND, OBS_TOTAL_A = 0, 1
 
@@ -21,6 +21,8 @@ EXPORTS = [
     "sprb200_simulate_raw", "sprb200_neighbor_table", "sprb200_build_slice", "sprb200_build_table",
     "sprb200_merge_slice", "sprb200_build_slice_device", "sprb200_scatter_table_device",
     "sprb200_build_indices_device", "sprb200_build_indices", "sprb200_scatter_rows_device",
+    "sprb200_deal_indices", "sprb200_build_table_multi", "sprb200_multi_stats", "sprb200_multi_release",
+    "sprb200_comm_unique_id", "sprb200_comm_init", "sprb200_comm_destroy", "sprb200_build_table_dist",
 ]
 
 
@@ -124,6 +126,22 @@ def load():
     L.sprb200_surrogate_load.argtypes = [vp, P(SprGrid), i32, dbl, dbl, vp, i32]
     L.sprb200_fit_loss.restype = C.c_int
     L.sprb200_fit_loss.argtypes = [vp, P(SprAligned), P(dbl), i64, P(dbl)]
+    L.sprb200_deal_indices.restype = i64
+    L.sprb200_deal_indices.argtypes = [P(SprGrid), P(SprSim), i32, i32, P(i64), i64]
+    L.sprb200_build_table_multi.restype = C.c_int
+    L.sprb200_build_table_multi.argtypes = [P(i32), i32, P(SprGrid), P(SprSim), P(SprRun), P(dbl), P(i32), P(u64)]
+    L.sprb200_multi_stats.restype = C.c_int
+    L.sprb200_multi_stats.argtypes = [P(i32), i32, P(u64), P(dbl), P(dbl)]
+    L.sprb200_multi_release.restype = None
+    L.sprb200_multi_release.argtypes = []
+    L.sprb200_comm_unique_id.restype = C.c_int
+    L.sprb200_comm_unique_id.argtypes = [P(C.c_ubyte)]
+    L.sprb200_comm_init.restype = C.c_int
+    L.sprb200_comm_init.argtypes = [vp, P(C.c_ubyte), i32, i32]
+    L.sprb200_comm_destroy.restype = C.c_int
+    L.sprb200_comm_destroy.argtypes = [vp]
+    L.sprb200_build_table_dist.restype = C.c_int
+    L.sprb200_build_table_dist.argtypes = [vp, P(SprGrid), P(SprSim), P(SprRun), P(dbl), vp, P(i32), P(u64)]
     if L.sprb200_abi_version() != ABI_VERSION:
         raise ImportError("libsprb200.so ABI version mismatch")
     _lib = L
@@ -156,6 +174,48 @@ def grid_points(grid, idx=None):
             raise SprB200Error(ERR_BAD_ARG, "index outside the grid")
         out[k] = (p.kon_eff, p.koff, p.konb, p.reach)
     return out
+
+
+def deal_indices(grid, sim, nranks, rank):
+    """1-based linear grid indices (ascending) that `rank` of `nranks` simulates: the library's own
+    cost-balanced deal (sprb200_deal_indices), the one sprb200_build_table_multi / _dist use."""
+    L = load()
+    n = L.sprb200_deal_indices(C.byref(grid), C.byref(sim.c), nranks, rank, None, 0)
+    if n < 0:
+        raise SprB200Error(int(n), "bad arguments to sprb200_deal_indices")
+    out = np.zeros(int(n), dtype=np.int64)
+    L.sprb200_deal_indices(C.byref(grid), C.byref(sim.c), nranks, rank, _ptr(out, C.c_int64), n)
+    return out
+
+
+def comm_unique_id():
+    """128 bytes identifying a new communicator (rank 0 creates it and hands it to every rank)."""
+    L = load()
+    buf = (C.c_ubyte * 128)()
+    rc = L.sprb200_comm_unique_id(buf)
+    if rc != OK:
+        raise SprB200Error(rc, L.sprb200_last_error(None).decode())
+    return bytes(buf)
+
+
+def build_table_multi(devices, grid, sim, run, want_counts=True):
+    """build_surrogate_serial on several GPUs of this process (sprb200_build_table_multi): returns
+    (table [T][P], n_used [P], n_events [P], per-device stats)."""
+    L = load()
+    dv = np.ascontiguousarray(devices, dtype=np.int32)
+    Pn = int(np.prod([grid.n[k] for k in range(4)]))
+    out = np.zeros((sim.T, Pn))
+    nu = np.zeros(Pn, dtype=np.int32) if want_counts else None
+    nev = np.zeros(Pn, dtype=np.uint64) if want_counts else None
+    rc = L.sprb200_build_table_multi(_ptr(dv, C.c_int32), len(dv), C.byref(grid), C.byref(sim.c), C.byref(run),
+                                     _ptr(out, C.c_double), _ptr(nu, C.c_int32), _ptr(nev, C.c_uint64))
+    if rc != OK:
+        raise SprB200Error(rc, L.sprb200_last_error(None).decode())
+    ev = np.zeros(len(dv), dtype=np.uint64)
+    ms = np.zeros(len(dv))
+    tms = np.zeros(len(dv))
+    L.sprb200_multi_stats(_ptr(dv, C.c_int32), len(dv), _ptr(ev, C.c_uint64), _ptr(ms, C.c_double), _ptr(tms, C.c_double))
+    return out, nu, nev, dict(events=ev, device_ms=ms, traj_ms=tms)
 
 
 def balanced_deal(costs, world):
@@ -356,6 +416,25 @@ class Engine:
         al = SprAligned(len(npts), _ptr(npts, C.c_int32), _ptr(tt, C.c_double), _ptr(vv, C.c_double), _ptr(abc, C.c_double))
         self._check(self.lib.sprb200_fit_loss(self.h, C.byref(al), _ptr(op, C.c_double), len(op), _ptr(loss, C.c_double)))
         return loss
+
+    def comm_init(self, unique_id, nranks, rank):
+        """joins the communicator `unique_id` (bytes from comm_unique_id) as `rank` of `nranks` (collective)"""
+        buf = (C.c_ubyte * 128)(*bytearray(unique_id)) if unique_id is not None else None
+        self._check(self.lib.sprb200_comm_init(self.h, buf, int(nranks), int(rank)))
+
+    def comm_destroy(self):
+        self._check(self.lib.sprb200_comm_destroy(self.h))
+
+    def build_table_dist(self, grid, sim, run, host=True, d_table=0, want_counts=True):
+        """collective build over the handle's communicator: (table [T][P] or None, n_used, n_events)"""
+        Pn = int(np.prod([grid.n[k] for k in range(4)]))
+        out = np.zeros((sim.T, Pn)) if host else None
+        nu = np.zeros(Pn, dtype=np.int32) if want_counts else None
+        nev = np.zeros(Pn, dtype=np.uint64) if want_counts else None
+        self._check(self.lib.sprb200_build_table_dist(self.h, C.byref(grid), C.byref(sim.c), C.byref(run),
+                                                      _ptr(out, C.c_double), C.c_void_p(d_table or None),
+                                                      _ptr(nu, C.c_int32), _ptr(nev, C.c_uint64)))
+        return out, nu, nev
 
     def scatter_table_device(self, d_rows, idxstart, stride, count, T, P, d_table):
         self._check(self.lib.sprb200_scatter_table_device(self.h, C.c_void_p(d_rows), idxstart, stride, count, T, P,

@@ -354,14 +354,36 @@ def _run_from_terminator(terminator, simpars, seed):
     raise TypeError("surrogate builds support SimNumberTerminator and VarianceTerminator")
 
 
-def build_surrogate_serial(surrogate_size, surpars, simpars, terminator=None, seed=None, device=0):
+def _device_list(device, devices):
+    """devices = None: the single `device`; "all": every visible GPU; else an explicit list of ordinals"""
+    if devices is None:
+        return [int(device)]
+    if isinstance(devices, str):
+        if devices != "all":
+            raise ValueError("devices must be None, 'all' or a list of device ordinals")
+        import ctypes
+        n = ctypes.c_int(0)
+        cudart = ctypes.CDLL("libcudart.so")
+        if cudart.cudaGetDeviceCount(ctypes.byref(n)) != 0 or n.value < 1:
+            raise _lib.SprB200Error(_lib.ERR_NO_DEVICE, "no CUDA device (libsprb200 has no CPU fallback)")
+        return list(range(n.value))
+    return [int(d) for d in devices]
+
+
+def build_surrogate_serial(surrogate_size, surpars, simpars, terminator=None, seed=None, device=0, devices=None):
     """surrogate.jl:203-242: the (nkon, nkoff, nkonb, nreach, ntime) table, returned as a Fortran-ordered
-    numpy array (same memory as Julia's Array{Float64,5})."""
+    numpy array (same memory as Julia's Array{Float64,5}).  devices = "all" or a list of GPU ordinals shares the
+    grid points among several GPUs of this process (sprb200_build_table_multi); the table is byte-identical
+    for any number of GPUs."""
     surrogate_size = tuple(int(v) for v in surrogate_size)
     assert surrogate_size[-1] == len(simpars.tsave)    # surrogate.jl:205
     seed = _next_seed() if seed is None else int(seed)
-    table, _, _ = get_engine(device).build_table(_grid(surpars, surrogate_size[:4]), simpars.spec(),
-                                                 _run_from_terminator(terminator, simpars, seed))
+    devs = _device_list(device, devices)
+    grid, run = _grid(surpars, surrogate_size[:4]), _run_from_terminator(terminator, simpars, seed)
+    if len(devs) > 1:
+        table = _lib.build_table_multi(devs, grid, simpars.spec(), run, want_counts=False)[0]
+    else:
+        table, _, _ = get_engine(devs[0]).build_table(grid, simpars.spec(), run)
     return table.reshape(-1).reshape(surrogate_size, order="F")
 
 
@@ -416,9 +438,10 @@ def save_surrogate_metadata(filename, sursize, surpars, simpars, seed=None):
     np.savez(_npz(filename), **d)
 
 
-def save_surrogate(filename, surrogate_size, surpars, simpars, terminator=None, seed=None, device=0):
+def save_surrogate(filename, surrogate_size, surpars, simpars, terminator=None, seed=None, device=0, devices=None):
     """surrogate.jl:151-158."""
-    table = build_surrogate_serial(surrogate_size, surpars, simpars, terminator=terminator, seed=seed, device=device)
+    table = build_surrogate_serial(surrogate_size, surpars, simpars, terminator=terminator, seed=seed, device=device,
+                                   devices=devices)
     np.savez(_npz(filename), FirstMoment=table, **_metadata_dict(surrogate_size, surpars, simpars))
 
 
@@ -736,18 +759,31 @@ def update_pars_and_run_spr_sim(outputter, logpars, simpars, seed=None, device=0
 def fitted_curves(optsol, aligneddat, simpars, seed=None, device=0):
     """the simulation half of visualisefit / savefit (fitting.jl:264-278, 331-345): for every antibody
     concentration, mean bound response of simpars.nsims forward simulations at the fitted parameters, saved at
-    the data times.  Returns a list of arrays aligned with aligneddat.times (plotting/XLSX are out of scope)."""
+    the data times.  Returns a list of arrays aligned with aligneddat.times (plotting/XLSX are out of scope).
+
+    The reference loops over the concentrations; here they are ONE batched GPU call (one parameter point per
+    concentration, the same replicate count for each), so that a few hundred replicates per curve still fill
+    the GPU.  Curves with different time grids are saved on the sorted union of the grids (a save slot records
+    the state at that instant, so sub-sampling it afterwards changes nothing)."""
     params = list(optsol.u if hasattr(optsol, "u") else optsol)
-    out = []
     abcref = aligneddat.antibodyconcens[0]
-    for i, abc in enumerate(aligneddat.antibodyconcens):
+    times = [np.asarray(t, dtype=np.float64) for t in aligneddat.times]
+    tall = np.unique(np.concatenate(times))
+    antigenconcen = inv_cubic_nm_to_muM(getantigenconcen(simpars))
+    pts, cps = [], []
+    for abc in aligneddat.antibodyconcens:
         ps = list(params)
-        ps[0] = params[0] + math.log10(abc / abcref)
-        o = TotalBoundOutputter(len(aligneddat.times[i]))
-        simpars.tsave = np.asarray(aligneddat.times[i], dtype=np.float64)
-        simpars.tstop = float(aligneddat.times[i][-1])
-        update_pars_and_run_spr_sim(o, ps, simpars, seed=None if seed is None else seed + i, device=device)
-        out.append(means(o))
+        ps[0] = params[0] + math.log10(abc / abcref)       # fitting.jl:273
+        bp = biopars_from_fitting_vec(ps, antigenconcen=antigenconcen, antibodyconcen=1.0)
+        pts.append(_point(bp))
+        cps.append(bp.CP)
+    simpars.tsave = tall                                    # fitting.jl:274 mutates simpars the same way
+    simpars.tstop = float(max(t[-1] for t in times))
+    run = _lib.make_run(nsims=simpars.nsims, seed=_next_seed() if seed is None else int(seed))
+    res = get_engine(device).simulate(simpars.spec(), pts, run, want=("mean",))
+    out = []
+    for i, t in enumerate(times):
+        out.append(cps[i] * res["mean"][i][np.searchsorted(tall, t)])
     return out
 
 

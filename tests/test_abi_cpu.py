@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for name in declared_functions():
         assert hasattr(L, name), name
     L.sprb200_abi_version.restype = C.c_int
-    assert L.sprb200_abi_version() == 1
+    assert L.sprb200_abi_version() == 2
 
 
 def test_no_cpu_fallback(built_lib):
@@ -132,3 +132,35 @@ def test_cost_balanced_deal(built_lib):
         assert sums.max() / sums.min() < 1.002
     # deterministic (every rank computes the same deal)
     assert all(np.array_equal(a, b) for a, b in zip(_lib.balanced_deal(cost, 8), _lib.balanced_deal(cost.copy(), 8)))
+
+
+def test_library_deal_matches_python_deal(built_lib):
+    """sprb200_deal_indices (what sprb200_build_table_multi / _dist use) == the Python statement of the same
+    rule; device-free; a partition for every rank count"""
+    import sprb200
+    from sprb200 import _lib
+    grid = _lib.make_grid((-5, 2), (-4, 0), (-3, 1.5), (2, 35), (7, 5, 4, 6))
+    sim = sprb200.SimSpec(1000, 3, _lib.domain_length(), 600.0, 150.0, np.linspace(0, 600, 601))
+    cost = _lib.estimate_cost(sim, _lib.grid_points(grid))
+    for world in (1, 2, 5, 8):
+        py = _lib.balanced_deal(cost, world)
+        mine = [_lib.deal_indices(grid, sim, world, r) for r in range(world)]
+        for r in range(world):
+            assert np.array_equal(mine[r], py[r] + 1)
+        assert np.array_equal(np.sort(np.concatenate(mine)), np.arange(1, 7 * 5 * 4 * 6 + 1))
+    with pytest.raises(_lib.SprB200Error):
+        _lib.deal_indices(grid, sim, 4, 4)
+
+
+def test_dist_entry_points_fail_loudly_without_gpu(built_lib):
+    """the multi-GPU entry points have no CPU path either"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import sprb200
+    from sprb200 import _lib
+    grid = _lib.make_grid((-3, 2), (-4, -1), (-3, 1.5), (2, 35), (2, 2, 2, 2))
+    sim = sprb200.SimSpec(100, 3, 50.0, 10.0, 5.0, np.linspace(0, 10, 11))
+    with pytest.raises(_lib.SprB200Error) as e:
+        _lib.build_table_multi([0], grid, sim, _lib.make_run(nsims=2))
+    assert e.value.code == _lib.ERR_NO_DEVICE

