@@ -20,43 +20,59 @@ def fake_rows(idx, T):
     return np.sin(0.001 * idx[:, None].astype(np.float64) * (s + 1.0))
 
 
-def _worker(rank, world, port, tmp):
+GRID_SIZE = (5, 3, 3, 3)          # 135 points: not divisible by 2 or 4, so the padded-slab path is exercised
+
+
+def _job():
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "sprfittingpaper2023.jl_b200"))
-    import bench
+    import sprb200
     from sprb200 import _lib
+    grid = _lib.make_grid((-3, 2), (-4, -1), (-3, 1.5), (2, 35), GRID_SIZE)
+    sim = sprb200.SimSpec(1000, 3, _lib.domain_length(), 600.0, 150.0, np.linspace(0, 600, 601))
+    return _lib, grid, sim
+
+
+def _worker(rank, world, port, tmp):
+    _lib, grid, sim = _job()
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     T = 7
-    idx = bench.rank_indices(world, rank)
-    rows = torch.from_numpy(fake_rows(idx, T))
+    # what sprb200_build_table_dist does on every rank: the library's deal, a slab padded to the largest share,
+    # one all-gather, a scatter that skips the padding rows (index 0)
+    deal = [_lib.deal_indices(grid, sim, world, r) for r in range(world)]
+    maxcount = max(len(d) for d in deal)
+    idx = deal[rank]
+    slab = np.zeros((maxcount, T))
+    slab[:len(idx)] = fake_rows(idx, T)
+    rows = torch.from_numpy(slab)
     gathered = [torch.empty_like(rows) for _ in range(world)]
     dist.all_gather(gathered, rows)
     all_rows = torch.cat(gathered).numpy()
-    idx_all = np.concatenate([bench.rank_indices(world, r) for r in range(world)])
-    P = len(idx_all)
-    grid = _lib.make_grid((-3, 2), (-4, -1), (-3, 1.5), (2, 35), bench.NK + (bench.NREACH_PER_GPU * world,))
+    idx_all = np.zeros(maxcount * world, dtype=np.int64)
+    for r in range(world):
+        idx_all[r * maxcount:r * maxcount + len(deal[r])] = deal[r]
+    P = int(np.prod(GRID_SIZE))
     table = np.zeros((T, P))
-    # host scatter = sprb200_merge_slice per run of consecutive indices (same arithmetic as the device scatter
-    # sprb200_scatter_rows_device: table[s*P + idx-1] = rows[k*T + s])
-    cuts = np.flatnonzero(np.diff(idx_all) != 1) + 1
-    for a, b in zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [len(idx_all)]])):
-        _lib.merge_slice(grid, T, all_rows[a:b], int(idx_all[a]), int(idx_all[b - 1]), table)
+    for k, i in enumerate(idx_all):
+        if i >= 1:     # sprb200_merge_slice: table[s*P + idx-1] = rows[k*T + s], the device scatter's arithmetic
+            _lib.merge_slice(grid, T, all_rows[k:k + 1], int(i), int(i), table)
     np.save(os.path.join(tmp, "table_%d.npy" % rank), table)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_rank_indices_partition():
-    sys.path.insert(0, ROOT)
-    import bench
+def test_rank_indices_partition(built_lib):
+    _lib, grid, sim = _job()
+    P = int(np.prod(GRID_SIZE))
     for world in (1, 2, 4, 8):
-        allidx = np.concatenate([bench.rank_indices(world, r) for r in range(world)])
-        P = bench.NK[0] * bench.NK[1] * bench.NK[2] * bench.NREACH_PER_GPU * world
+        deal = [_lib.deal_indices(grid, sim, world, r) for r in range(world)]
+        allidx = np.concatenate(deal)
         assert len(allidx) == P and np.array_equal(np.sort(allidx), np.arange(1, P + 1))
-        sizes = {len(bench.rank_indices(world, r)) for r in range(world)}
-        assert sizes == {P // world}                       # equal slabs (all_gather needs them)
+        sizes = [len(d) for d in deal]
+        assert max(sizes) - min(sizes) <= 1
+        assert all(np.all(np.diff(d) > 0) for d in deal)
 
 
 def test_two_rank_gather_equals_single_rank(built_lib, tmp_path):
