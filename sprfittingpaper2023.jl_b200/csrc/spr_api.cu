@@ -91,7 +91,6 @@ struct sprb200_ctx {
     double sur_t0 = 0.0, sur_t1 = 0.0;
     long long sur_P = 0;
     int stage_cap_override = 0;   // SPRB200_STAGE_CAP (test hook): staging stride of K2's distance pass
-    int k1_variant = 5;       // SPRB200_K1_VARIANT (experiment hook): trajectory-kernel instantiation (4 or 5)
 };
 
 namespace {
@@ -167,7 +166,10 @@ size_t record_estimate(int N, int DIM, double L, double reach, double scale) {
     double ent = (E + 3.0 * std::sqrt(2.0 * E) + 32.0) * scale;
     const double maxe = (double)N * (double)(N - 1);
     if (ent > maxe) ent = maxe;
-    return record_bytes(N, (unsigned long long)std::ceil(ent));
+    // packed rows: entries_per_word(N) entries per word, every row rounded up to a whole word
+    const double epw = (double)entries_per_word(N);
+    const double words = ent / epw + (double)N * (epw - 1.0) / epw * (E > 0.0 ? std::min(1.0, E / (double)N) : 0.0);
+    return record_bytes(N, (unsigned long long)std::ceil(words));
 }
 
 // rough SSA event count of one trajectory (only used to start expensive points first)
@@ -196,7 +198,7 @@ struct RunPlan {
 // one fixed-position neighbour table (K2b) in record format; the caller owns `rec`
 struct FixedGraph {
     unsigned char *rec = nullptr;
-    long long entries = 0;
+    long long words = 0;
     unsigned int maxdeg = 0;
 };
 
@@ -207,27 +209,26 @@ int build_fixed_graph(sprb200_ctx *h, const SprSim *sim, double reach, FixedGrap
     CUDA_TRY(h, h->goff.ensure(sizeof(uint32_t) * (N + 1)));
     CUDA_TRY(h, h->misc.ensure(64));
     CUDA_TRY(h, cudaMemsetAsync(h->misc.p, 0, 64, s0));
-    CUDA_TRY(h, launch_fixed_graph(h->locs.as<double>(), N, DIM, sim->L, reach, h->goff.as<uint32_t>(), nullptr, 0,
+    CUDA_TRY(h, launch_fixed_graph(h->locs.as<double>(), N, DIM, sim->L, reach, h->goff.as<uint32_t>(), nullptr,
                                    h->misc.as<unsigned long long>(),
                                    reinterpret_cast<unsigned int *>(h->misc.as<unsigned long long>() + 1), s0));
     unsigned long long res[2] = {0, 0};
     CUDA_TRY(h, cudaMemcpyAsync(res, h->misc.p, sizeof(res), cudaMemcpyDeviceToHost, s0));
     CUDA_TRY(h, cudaStreamSynchronize(s0));
     h->st_launches += 2;
-    g->entries = (long long)res[0];
+    g->words = (long long)res[0];
     g->maxdeg = (unsigned int)(res[1] & 0xffffffffu);
-    const size_t bytes = record_bytes(N, (unsigned long long)g->entries);
+    const size_t bytes = record_bytes(N, (unsigned long long)g->words);
     void *p = nullptr;
     if (cudaMalloc(&p, bytes) != cudaSuccess) {
         cudaGetLastError();
         return fail(h, SPRB200_ERR_ALLOC, "cudaMalloc(fixed graph record)");
     }
     g->rec = static_cast<unsigned char *>(p);
-    uint16_t *nbr = reinterpret_cast<uint16_t *>(g->rec + align16z(sizeof(uint32_t) * (size_t)(N + 1)));
+    uint32_t *words = reinterpret_cast<uint32_t *>(g->rec + align16z(sizeof(uint32_t) * (size_t)(N + 1)));
     cudaError_t e = cudaMemcpyAsync(g->rec, h->goff.p, sizeof(uint32_t) * (N + 1), cudaMemcpyDeviceToDevice, s0);
-    if (e == cudaSuccess)
-        e = launch_fixed_graph(h->locs.as<double>(), N, DIM, sim->L, reach, h->goff.as<uint32_t>(), nbr, g->entries,
-                               nullptr, nullptr, s0);
+    if (e == cudaSuccess && g->words > 0)
+        e = launch_fixed_graph(h->locs.as<double>(), N, DIM, sim->L, reach, h->goff.as<uint32_t>(), words, nullptr, nullptr, s0);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s0);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -237,6 +238,22 @@ int build_fixed_graph(sprb200_ctx *h, const SprSim *sim, double reach, FixedGrap
     }
     h->st_launches += 1;
     return SPRB200_OK;
+}
+
+// CSR form (offsets in entries, neighbour indices) of a packed record copied to the host: test hook only
+void unpack_record(int N, const uint32_t *offw, const uint32_t *words, std::vector<uint32_t> *off, std::vector<uint32_t> *nbr) {
+    const int eb = entry_bits(N), epw = entries_per_word(N);
+    const uint32_t empty = (1u << eb) - 1u;
+    off->assign((size_t)N + 1, 0u);
+    nbr->clear();
+    for (int i = 0; i < N; ++i) {
+        for (uint32_t w = offw[i]; w < offw[i + 1]; ++w)
+            for (int e = 0; e < epw; ++e) {
+                const uint32_t j = (words[w] >> (e * eb)) & empty;
+                if (j != empty) nbr->push_back(j);
+            }
+        (*off)[(size_t)i + 1] = (uint32_t)nbr->size();
+    }
 }
 
 // Simulates `npts` points (already on the host as PointDev + pidx).  On return the device arenas hold
@@ -362,7 +379,7 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                 const FixedGraph &g = graphs[pts[b0 + k].reach];
                 h_slotrec[k] = (unsigned long long)(uintptr_t)g.rec;
                 fixed_maxdeg = std::max(fixed_maxdeg, g.maxdeg);
-                fixed_maxent = std::max(fixed_maxent, g.entries);
+                fixed_maxent = std::max(fixed_maxent, g.words);
             }
             CUDA_TRY(h, cudaMemcpyAsync(h->slotrec.p, h_slotrec.data(), sizeof(unsigned long long) * nb,
                                         cudaMemcpyHostToDevice, s0));
@@ -416,7 +433,7 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                     CUDA_TRY(h, cudaMemcpyAsync(h->tickets.p, deferred.data(), sizeof(long long) * deferred.size(),
                                                 cudaMemcpyHostToDevice, s0));
                     for (long long t : deferred) want += 2 * h_est[(size_t)(t / nrep)] + 4096;
-                    want = std::max(want, record_bytes(N, (unsigned long long)N * (unsigned long long)(N - 1)));
+                    want = std::max(want, record_bytes(N, (unsigned long long)N * (unsigned long long)((N - 1 + entries_per_word(N) - 1) / entries_per_word(N))));
                 } else if (fixedpos) {
                     n = ntick_total;
                     tk = ntick_total;
@@ -456,6 +473,7 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                     ta.spos_out = nullptr;
                     ta.stage = h->stage.as<uint16_t>();
                     ta.stage_cap = stage_cap;
+                    ta.epw = entries_per_word(N); ta.eb = entry_bits(N);
                     const long long nblk = std::min<long long>(n, (long long)k2_ctas * h->num_sms);
                     cudaEvent_t ea = h->next_event(), eb = h->next_event();
                     if (ea && eb) cudaEventRecord(ea, s0);
@@ -483,17 +501,31 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                 if (ndefer < n) {
                     TrajLayout lay;
                     const bool wide_sn = ctr[CTR_MAX_DEGREE] > 127ULL, wide_off = ctr[CTR_MAX_ENTRIES] > 65535ULL;
-                    if (!make_traj_layout(N, wide_sn, wide_off, h->smem_optin, h->smem_per_sm, &lay, h->k1_variant)) {
+                    if (!make_traj_layout(N, wide_sn, wide_off, h->smem_optin, h->smem_per_sm, &lay)) {
                         free_graphs();
                         return fail(h, SPRB200_ERR_TOO_LARGE,
                                     "per-trajectory state (N=" + std::to_string(N) + ", max degree " +
                                         std::to_string(ctr[CTR_MAX_DEGREE]) + ", " + std::to_string(ctr[CTR_MAX_ENTRIES]) +
-                                        " table entries) needs " + std::to_string(lay.slice) +
+                                        " table words) needs " + std::to_string(lay.slice) +
                                         " B of shared memory, limit " + std::to_string(h->smem_optin));
                     }
                     if (h->max_warps > 0 && lay.cta_per_sm * lay.wpc > h->max_warps) {
                         if (h->max_warps < lay.wpc) lay.wpc = h->max_warps;
                         lay.cta_per_sm = std::max(1, h->max_warps / lay.wpc);
+                    }
+                    // a launch that cannot fill the GPU (C1 / C4 / post-fit re-simulation: a few hundred to a few
+                    // thousand trajectories) runs narrower CTAs, so that the block scheduler spreads the warps
+                    // evenly over all SMs and their four schedulers instead of stacking 7 per CTA
+                    {
+                        const long long full = (long long)lay.cta_per_sm * lay.wpc * h->num_sms;
+                        if (n < full) {
+                            const long long per_sm = (n + h->num_sms - 1) / h->num_sms;      // warps per SM if spread evenly
+                            int w = (int)std::max<long long>(1, per_sm / 4);                 // at least 4 CTAs per SM
+                            if (w < lay.wpc) {
+                                lay.cta_per_sm = std::min(32, (lay.cta_per_sm * lay.wpc) / w);
+                                lay.wpc = w;
+                            }
+                        }
                     }
                     TrajArgs a{};
                     a.N = N; a.T = T; a.tstop = sim->tstop;
@@ -775,7 +807,6 @@ int sprb200_create(int device_ordinal, sprb200_handle *out) {
     }
     if (const char *env = std::getenv("SPRB200_MAX_WARPS")) h->max_warps = std::atoi(env);
     if (const char *env = std::getenv("SPRB200_STAGE_CAP")) h->stage_cap_override = std::atoi(env);
-    if (const char *env = std::getenv("SPRB200_K1_VARIANT")) h->k1_variant = std::atoi(env) == 4 ? 4 : 5;
     if (const char *env = std::getenv("SPRB200_CAP_SCALE")) {
         const double v = std::atof(env);
         if (v > 0.0 && v <= 1.0) h->est_scale = v;
@@ -945,21 +976,20 @@ int64_t sprb200_neighbor_table(sprb200_handle h, const SprSim *sim, double reach
     const int N = sim->N, DIM = sim->DIM;
     cudaStream_t s0 = h->stream[0];
     CUDA_TRY(h, cudaSetDevice(h->device));
-    std::vector<uint32_t> off(N + 1);
-    std::vector<uint16_t> nbr;
-    long long total = 0;
-    const size_t o_nbr = align16z(sizeof(uint32_t) * (size_t)(N + 1));
+    std::vector<uint32_t> offw(N + 1), words, off, nbr;
+    const size_t o_words = align16z(sizeof(uint32_t) * (size_t)(N + 1));
+    const unsigned long long maxwords =
+        (unsigned long long)N * (unsigned long long)((N - 1 + entries_per_word(N) - 1) / entries_per_word(N));
     if (!sim->resample_initlocs) {
         CUDA_TRY(h, h->locs.ensure(sizeof(double) * N * DIM));
         CUDA_TRY(h, cudaMemcpyAsync(h->locs.p, sim->initlocs, sizeof(double) * N * DIM, cudaMemcpyHostToDevice, s0));
         FixedGraph g;
         rc = build_fixed_graph(h, sim, reach, &g);
         if (rc) return rc;
-        total = g.entries;
-        nbr.resize((size_t)std::max<long long>(total, 1));
-        cudaError_t e = cudaMemcpyAsync(off.data(), g.rec, sizeof(uint32_t) * (N + 1), cudaMemcpyDeviceToHost, s0);
-        if (e == cudaSuccess && total > 0)
-            e = cudaMemcpyAsync(nbr.data(), g.rec + o_nbr, sizeof(uint16_t) * total, cudaMemcpyDeviceToHost, s0);
+        words.resize((size_t)std::max<long long>(g.words, 1));
+        cudaError_t e = cudaMemcpyAsync(offw.data(), g.rec, sizeof(uint32_t) * (N + 1), cudaMemcpyDeviceToHost, s0);
+        if (e == cudaSuccess && g.words > 0)
+            e = cudaMemcpyAsync(words.data(), g.rec + o_words, sizeof(uint32_t) * g.words, cudaMemcpyDeviceToHost, s0);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s0);
         cudaFree(g.rec);
         if (e != cudaSuccess) { cudaGetLastError(); return fail(h, SPRB200_ERR_CUDA, std::string("fixed graph copy: ") + cudaGetErrorString(e)); }
@@ -971,7 +1001,7 @@ int64_t sprb200_neighbor_table(sprb200_handle h, const SprSim *sim, double reach
         PointDev p{0, 0, 0, reach};
         const uint32_t pi = (uint32_t)param_index;
         const int32_t ord = 0;
-        const size_t recmax = record_bytes(N, (unsigned long long)N * (unsigned long long)(N - 1));
+        const size_t recmax = record_bytes(N, maxwords);
         CUDA_TRY(h, h->pts.ensure(sizeof(PointDev)));
         CUDA_TRY(h, h->pidx.ensure(sizeof(uint32_t)));
         CUDA_TRY(h, h->order.ensure(sizeof(int32_t)));
@@ -995,6 +1025,8 @@ int64_t sprb200_neighbor_table(sprb200_handle h, const SprSim *sim, double reach
         ta.desc = h->desc.as<unsigned long long>(); ta.defer_list = h->defer.as<long long>();
         ta.spos_out = h->locs.as<uint64_t>();
         ta.stage_cap = table_stage_cap(N, DIM, sim->L, reach);
+        if (h->stage_cap_override > 0) ta.stage_cap = std::max(1, std::min(ta.stage_cap, h->stage_cap_override));
+        ta.epw = entries_per_word(N); ta.eb = entry_bits(N);
         CUDA_TRY(h, h->stage.ensure(sizeof(uint16_t) * (size_t)N * (size_t)ta.stage_cap));
         ta.stage = h->stage.as<uint16_t>();
         CUDA_TRY(h, launch_table(ta, DIM, 1, s0));
@@ -1002,12 +1034,12 @@ int64_t sprb200_neighbor_table(sprb200_handle h, const SprSim *sim, double reach
         CUDA_TRY(h, cudaMemcpyAsync(ctr, h->counters.p, sizeof(ctr), cudaMemcpyDeviceToHost, s0));
         CUDA_TRY(h, cudaStreamSynchronize(s0));
         if (ctr[CTR_NDEFER] != 0) return fail(h, SPRB200_ERR_INTERNAL, "table did not fit a full-size arena");
-        total = (long long)ctr[CTR_MAX_ENTRIES];
-        nbr.resize((size_t)std::max<long long>(total, 1));
+        const long long nwords = (long long)ctr[CTR_MAX_ENTRIES];
+        words.resize((size_t)std::max<long long>(nwords, 1));
         std::vector<uint64_t> spos((size_t)N);
-        CUDA_TRY(h, cudaMemcpyAsync(off.data(), h->arena.p, sizeof(uint32_t) * (N + 1), cudaMemcpyDeviceToHost, s0));
-        if (total > 0)
-            CUDA_TRY(h, cudaMemcpyAsync(nbr.data(), h->arena.as<unsigned char>() + o_nbr, sizeof(uint16_t) * total, cudaMemcpyDeviceToHost, s0));
+        CUDA_TRY(h, cudaMemcpyAsync(offw.data(), h->arena.p, sizeof(uint32_t) * (N + 1), cudaMemcpyDeviceToHost, s0));
+        if (nwords > 0)
+            CUDA_TRY(h, cudaMemcpyAsync(words.data(), h->arena.as<unsigned char>() + o_words, sizeof(uint32_t) * nwords, cudaMemcpyDeviceToHost, s0));
         CUDA_TRY(h, cudaMemcpyAsync(spos.data(), h->locs.p, sizeof(uint64_t) * N, cudaMemcpyDeviceToHost, s0));
         CUDA_TRY(h, cudaStreamSynchronize(s0));
         if (positions_out) {
@@ -1017,9 +1049,11 @@ int64_t sprb200_neighbor_table(sprb200_handle h, const SprSim *sim, double reach
                     positions_out[(size_t)i * DIM + d] = (double)((spos[i] >> (21 * d)) & 0x1fffffu) * scale;
         }
     }
+    unpack_record(N, offw.data(), words.data(), &off, &nbr);
+    const long long total = (long long)nbr.size();
     for (int i = 0; i <= N; ++i) off_out[i] = (int32_t)off[i];
     if (nbr_out)
-        for (long long q = 0; q < total && q < nbr_cap; ++q) nbr_out[q] = nbr[q];
+        for (long long q = 0; q < total && q < nbr_cap; ++q) nbr_out[q] = (int32_t)nbr[q];
     return total;
 }
 

@@ -92,11 +92,35 @@ __host__ __device__ inline int k2_stage_cap(int N, int DIM, double L, double rea
     return cap < 8 ? 8 : cap;
 }
 
-// MODE 0: count + stage (hits beyond `cap` are only counted); MODE 1: write every hit to `row`
+// Packed neighbour rows (the record K1 reads): EPW entries of EB bits per 32-bit word, rows start on a word,
+// the last word of a row is padded with the all-ones entry EMPTY.  EB = 10 (3 per word) when N <= 1023,
+// else 16 (2 per word).
+struct RowPacker {
+    uint32_t *w;        // next word of the row
+    uint32_t acc;       // word under construction
+    int fill, epw, eb;  // entries in acc
+    __device__ __forceinline__ void push(uint32_t j) {
+        acc |= j << (fill * eb);
+        if (++fill == epw) {
+            *w++ = acc;
+            acc = 0u;
+            fill = 0;
+        }
+    }
+    __device__ __forceinline__ void flush() {
+        if (fill) {
+            const uint32_t empty = (1u << eb) - 1u;
+            for (; fill < epw; ++fill) acc |= empty << (fill * eb);
+            *w++ = acc;
+        }
+    }
+};
+
+// MODE 0: count + stage (hits beyond `cap` are only counted); MODE 1: pack every hit into the record
 template <int DIM, int MODE>
 __device__ __forceinline__ int scan_range(int i, uint32_t xi, uint32_t yi, uint32_t zi, int j0, int j1,
                                           const uint4 *__restrict__ p, unsigned long long r2s, uint16_t *row, int cap,
-                                          int cnt) {
+                                          RowPacker &pk, int cnt) {
 #pragma unroll 1
     for (int j = j0; j < j1; ++j) {
         const uint4 c = p[j];
@@ -112,7 +136,8 @@ __device__ __forceinline__ int scan_range(int i, uint32_t xi, uint32_t yi, uint3
             acc += (unsigned long long)m * m;
         }
         if (acc <= r2s && j != i) {
-            if (MODE == 1 || cnt < cap) row[cnt] = (uint16_t)j;
+            if (MODE == 1) pk.push((uint32_t)j);
+            else if (cnt < cap) row[cnt] = (uint16_t)j;
             ++cnt;
         }
     }
@@ -122,10 +147,10 @@ __device__ __forceinline__ int scan_range(int i, uint32_t xi, uint32_t yi, uint3
 // all within-reach neighbours of sorted particle i, in the order of the specification
 template <int DIM, int MODE>
 __device__ __forceinline__ int particle_row(int i, int N, int nc, const K2Smem &s, unsigned long long r2s,
-                                            uint16_t *row, int cap) {
+                                            uint16_t *row, int cap, RowPacker &pk) {
     const uint4 me = s.p[i];
     const uint32_t xi = me.x, yi = me.y, zi = DIM == 3 ? me.z : 0u;
-    if (nc < 3) return scan_range<DIM, MODE>(i, xi, yi, zi, 0, N, s.p, r2s, row, cap, 0);
+    if (nc < 3) return scan_range<DIM, MODE>(i, xi, yi, zi, 0, N, s.p, r2s, row, cap, pk, 0);
     const uint32_t *cs1 = s.cs + 1;                     // cs1[c] = first sorted index of cell c
     const int cx = (int)__umulhi(xi, (uint32_t)nc);     // (k << 11) * nc >> 32 == (k * nc) >> 21
     const int cy = (int)__umulhi(yi, (uint32_t)nc);
@@ -149,9 +174,9 @@ __device__ __forceinline__ int particle_row(int i, int N, int nc, const K2Smem &
             int yy = cy + dy;
             yy = yy < 0 ? yy + nc : (yy >= nc ? yy - nc : yy);
             const int rb = (zz * nc + yy) * nc;
-            cnt = scan_range<DIM, MODE>(i, xi, yi, zi, (int)cs1[rb + ax1], (int)cs1[rb + bx1], s.p, r2s, row, cap, cnt);
+            cnt = scan_range<DIM, MODE>(i, xi, yi, zi, (int)cs1[rb + ax1], (int)cs1[rb + bx1], s.p, r2s, row, cap, pk, cnt);
             if (bx2 > ax2)
-                cnt = scan_range<DIM, MODE>(i, xi, yi, zi, (int)cs1[rb + ax2], (int)cs1[rb + bx2], s.p, r2s, row, cap, cnt);
+                cnt = scan_range<DIM, MODE>(i, xi, yi, zi, (int)cs1[rb + ax2], (int)cs1[rb + bx2], s.p, r2s, row, cap, pk, cnt);
         }
     }
     return cnt;
@@ -254,8 +279,10 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(cons
         // ---- 4. the distance pass (tmp is dead: off aliases it)
         unsigned int mydeg = 0u;
         for (int i = tid; i < N; i += K2_THREADS) {
-            const int c = particle_row<DIM, 0>(i, N, nc, s, r2s, stage + (size_t)i * (size_t)a.stage_cap, cap);
-            s.off[i + 1] = (uint32_t)c;
+            RowPacker none{nullptr, 0u, 0, 1, 16};
+            const int c = particle_row<DIM, 0>(i, N, nc, s, r2s, stage + (size_t)i * (size_t)a.stage_cap, cap, none);
+            s.seg[i] = (uint16_t)c;                       // degree (seg is dead after the sort)
+            s.off[i + 1] = (uint32_t)((c + a.epw - 1) / a.epw);   // words of the packed row
             mydeg = max(mydeg, (unsigned int)c);
         }
         mydeg = __reduce_max_sync(FULL, mydeg);
@@ -263,7 +290,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(cons
         __syncthreads();
         // ---- 5. offsets and the record
         if (warp == 0) {
-            // inclusive scan of the degrees in place: off[0] = 0, off[i+1] = entries of particles 0..i
+            // inclusive scan of the row lengths (words) in place: off[0] = 0, off[i+1] = words of particles 0..i
             const int per = (N + 31) >> 5;
             const int b = lane * per, e = min(b + per, N);
             unsigned int sum = 0;
@@ -279,7 +306,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(cons
                 // exactly-sized record from the arena (bump allocation)
                 const unsigned long long total = s.off[N];
                 const unsigned long long bytes = (unsigned long long)(((size_t)(N + 1) * 4 + 15) & ~(size_t)15) +
-                                                 ((total * 2ULL + 15ULL) & ~15ULL);
+                                                 ((total * 4ULL + 15ULL) & ~15ULL);
                 const unsigned long long at = atomicAdd(a.ctr + CTR_CURSOR, bytes);
                 if (at + bytes <= a.arena_bytes) {
                     s_base = at;
@@ -297,18 +324,24 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(cons
         __syncthreads();
         const unsigned long long at = s_base;
         if (at == ~0ULL) continue;
-        // ---- 6. the record: offsets, then the staged rows compacted (or recomputed when a row overflowed its stride)
+        // ---- 6. the record: word offsets, then the staged rows packed (or recomputed when a row overflowed its stride)
         uint32_t *goff = reinterpret_cast<uint32_t *>(a.arena + at);
-        uint16_t *gnbr = reinterpret_cast<uint16_t *>(a.arena + at + (((size_t)(N + 1) * 4 + 15) & ~(size_t)15));
+        uint32_t *gw = reinterpret_cast<uint32_t *>(a.arena + at + (((size_t)(N + 1) * 4 + 15) & ~(size_t)15));
         for (int i = tid; i <= N; i += K2_THREADS) goff[i] = s.off[i];
         if ((int)s_maxdeg <= cap) {
             for (int i = tid; i < N; i += K2_THREADS) {
-                const uint32_t o0 = s.off[i], dg = s.off[i + 1] - o0;
+                const int dg = (int)s.seg[i];
                 const uint16_t *src = stage + (size_t)i * (size_t)a.stage_cap;
-                for (uint32_t k = 0; k < dg; ++k) gnbr[o0 + k] = src[k];
+                RowPacker pk{gw + s.off[i], 0u, 0, a.epw, a.eb};
+                for (int k = 0; k < dg; ++k) pk.push((uint32_t)src[k]);
+                pk.flush();
             }
         } else {
-            for (int i = tid; i < N; i += K2_THREADS) particle_row<DIM, 1>(i, N, nc, s, r2s, gnbr + s.off[i], 0);
+            for (int i = tid; i < N; i += K2_THREADS) {
+                RowPacker pk{gw + s.off[i], 0u, 0, a.epw, a.eb};
+                particle_row<DIM, 1>(i, N, nc, s, r2s, nullptr, 0, pk);
+                pk.flush();
+            }
         }
         if (a.spos_out && q == 0) {
             for (int i = tid; i < N; i += K2_THREADS) {
@@ -325,70 +358,91 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(cons
 // lanes share the neighbour updates, list scans, save-slot writes and random-number generation.
 // State word of a particle: state | nA << 2 | nB << (2 + CB), CB = 7 (uint16_t) or 15 (uint32_t) bits
 // per neighbour count; state codes follow the reference (forward_simulator.jl:123).
+//
+// Shared memory of one trajectory, 8 bytes per particle (TrajLayout):
+//   off[N+1]  first word of every packed neighbour row        sn[N]  state words
+//   ab[N]     A list from the front, B list from the back and -- inside the gap between them, which always
+//             holds 2C free slots because A + B + 2C = N -- the complex list (one member per complex)
+//   pos[N]    A/B: index in its list; C: the partner
+// The neighbour rows themselves stay in the record in global memory (L2): EPW entries of EB bits per word.
 // ------------------------------------------------------------------------------------------------
 template <typename SnT> struct SnTraits;
 template <> struct SnTraits<uint16_t> { static constexpr int SH_A = 2, SH_B = 9; static constexpr uint32_t MASK = 0x7fu; };
 template <> struct SnTraits<uint32_t> { static constexpr int SH_A = 2, SH_B = 17; static constexpr uint32_t MASK = 0x7fffu; };
 
-// Neighbour updates are split into a load (row offset, degree, this lane's neighbour) and an apply
+// EB = 10: three entries per word, lanes 0..29 take the entries of 10 words per pass; EB = 16: two per word, 32
+// lanes take 16 words per pass.  A lane's word (lw) and shift (ls) inside a pass are constants of the lane.
+template <int EB> struct PackTraits {
+    static constexpr int EPW = EB == 10 ? 3 : 2;
+    static constexpr int WPP = 32 / EPW;               // words per pass
+    static constexpr uint32_t EMPTY = (1u << EB) - 1u;
+};
+
+// Neighbour updates are split into a load (row offset, length, this lane's neighbour) and an apply
 // (read-modify-write of the neighbour's state word), so that the loads of both members of a pair
 // event are in flight together.  When the partner of a pair event (`other`) is met, its own state
 // change `extra` rides on the same store: pair events need no separate state write.
 struct NbrRow {
-    int o0, dg, j;   // first entry, degree, neighbour handled by this lane (valid if lane < dg)
+    int o0, nw;      // first word, number of words
+    uint32_t j;      // neighbour handled by this lane in the first pass, EMPTY if none
 };
 
-// table entries are written by K2 (an earlier launch) and only read here
-__device__ __forceinline__ int ld_nbr(const uint16_t *__restrict__ nbr, uint32_t q) {
-    return (int)__ldg(nbr + q);
+// table words are written by K2 (an earlier launch) and only read here
+template <int EB>
+__device__ __forceinline__ uint32_t ld_entry(const uint32_t *__restrict__ words, int o0, int nw, int wi, int ls) {
+    uint32_t w = 0xffffffffu;                          // every entry EMPTY
+    if (wi < nw) w = __ldg(words + (uint32_t)(o0 + wi));
+    return (w >> ls) & PackTraits<EB>::EMPTY;
 }
 
-template <typename OffT>
-__device__ __forceinline__ NbrRow load_row(const uint16_t *__restrict__ nbr, const OffT *off, int m, int lane) {
+template <typename OffT, int EB>
+__device__ __forceinline__ NbrRow load_row(const uint32_t *__restrict__ words, const OffT *off, int m, int lw, int ls) {
     NbrRow r;
     r.o0 = (int)off[m];
-    r.dg = (int)off[m + 1] - r.o0;
-    r.j = lane < r.dg ? ld_nbr(nbr, (uint32_t)(r.o0 + lane)) : 0;
+    r.nw = (int)off[m + 1] - r.o0;
+    r.j = ld_entry<EB>(words, r.o0, r.nw, lw, ls);
     return r;
 }
 
 // sn[j] += delta for every neighbour j of the row; the neighbour `other` (the partner of a pair event)
-// also takes `extra`, its own state change: pair events need no separate state write.
-// apply_row covers the first 32 neighbours (one per lane), apply_row_tail the rest (degree > 32: rare).
-template <bool PAIR, typename SnT>
-__device__ __forceinline__ void apply_row(SnT *sn, const NbrRow &r, uint32_t delta, int other, uint32_t extra, int lane) {
-    if (lane < r.dg) {
+// also takes `extra`, its own state change.  apply_row covers the first pass (one neighbour per lane),
+// apply_row_tail the rest (more than WPP words: rare).
+template <bool PAIR, typename SnT, int EB>
+__device__ __forceinline__ void apply_row(SnT *sn, const NbrRow &r, uint32_t delta, uint32_t other, uint32_t extra) {
+    if (r.j != PackTraits<EB>::EMPTY) {
         uint32_t d = delta;
         if (PAIR && r.j == other) d += extra;
         sn[r.j] = (SnT)((uint32_t)sn[r.j] + d);
     }
 }
 
-template <bool PAIR, typename SnT>
-__device__ __forceinline__ void apply_row_tail(SnT *sn, const uint16_t *__restrict__ nbr, const NbrRow &r, uint32_t delta,
-                                               int other, uint32_t extra, int lane) {
+template <bool PAIR, typename SnT, int EB>
+__device__ __forceinline__ void apply_row_tail(SnT *sn, const uint32_t *__restrict__ words, const NbrRow &r, uint32_t delta,
+                                               uint32_t other, uint32_t extra, int lw, int ls) {
 #pragma unroll 1
-    for (int q = lane + 32; q < r.dg; q += 32) {
-        const int j = ld_nbr(nbr, (uint32_t)(r.o0 + q));
-        uint32_t d = delta;
-        if (PAIR && j == other) d += extra;
-        sn[j] = (SnT)((uint32_t)sn[j] + d);
+    for (int wi = lw + PackTraits<EB>::WPP; wi < r.nw; wi += PackTraits<EB>::WPP) {
+        const uint32_t j = ld_entry<EB>(words, r.o0, r.nw, wi, ls);
+        if (j != PackTraits<EB>::EMPTY) {
+            uint32_t d = delta;
+            if (PAIR && j == other) d += extra;
+            sn[j] = (SnT)((uint32_t)sn[j] + d);
+        }
     }
 }
 
 // both rows of a pair event: every phase touches each state word at most once and the phases are separated
 // by __syncwarp(), so the order of the additions is immaterial; ONE uniform branch covers both tails
-template <typename SnT>
-__device__ __forceinline__ void apply_pair(SnT *sn, const uint16_t *__restrict__ nbr, const NbrRow &ra, const NbrRow &rb,
-                                           uint32_t da, uint32_t db, int ma, int mb, uint32_t ea, uint32_t eb, int lane) {
-    apply_row<true, SnT>(sn, ra, da, mb, ea, lane);
+template <typename SnT, int EB>
+__device__ __forceinline__ void apply_pair(SnT *sn, const uint32_t *__restrict__ words, const NbrRow &ra, const NbrRow &rb,
+                                           uint32_t da, uint32_t db, int ma, int mb, uint32_t ea, uint32_t eb, int lw, int ls) {
+    apply_row<true, SnT, EB>(sn, ra, da, (uint32_t)mb, ea);
     __syncwarp();
-    apply_row<true, SnT>(sn, rb, db, ma, eb, lane);
+    apply_row<true, SnT, EB>(sn, rb, db, (uint32_t)ma, eb);
     __syncwarp();
-    if (__builtin_expect((ra.dg | rb.dg) > 32, 0)) {
-        apply_row_tail<true, SnT>(sn, nbr, ra, da, mb, ea, lane);
+    if (__builtin_expect(max(ra.nw, rb.nw) > PackTraits<EB>::WPP, 0)) {
+        apply_row_tail<true, SnT, EB>(sn, words, ra, da, (uint32_t)mb, ea, lw, ls);
         __syncwarp();
-        apply_row_tail<true, SnT>(sn, nbr, rb, db, ma, eb, lane);
+        apply_row_tail<true, SnT, EB>(sn, words, rb, db, (uint32_t)ma, eb, lw, ls);
         __syncwarp();
     }
 }
@@ -410,22 +464,56 @@ __device__ __forceinline__ int scan_small(int v, int lane, int nact) {
     return v;
 }
 
-// WPC = 5: 5 warps per CTA, 5 CTAs per SM (25 trajectories, 72 registers);
-// WPC = 4: 4 warps per CTA, 6 CTAs per SM (24 trajectories, 80 registers: measured 1-3 % slower, kept as the
-// SPRB200_K1_VARIANT=4 experiment hook)
-template <typename SnT, typename OffT, int WPC>
-__global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(const TrajArgs a) {
+// The complex list lives in ab[cs .. cs+C), inside the gap between the A list (front) and the B list (back).
+// [lo, hi) is the gap as it will be once the list appends of the current event are done; the block is moved
+// (rarely: it is re-aligned to the side the gap is drifting away from) only when it would collide.
+__device__ __forceinline__ int cl_make_room(uint16_t *ab, int cs, int C, int lo, int hi, int lane) {
+    if (C == 0 || (cs >= lo && cs + C <= hi)) return cs;
+    const int ns = cs < lo ? hi - C : lo;
+    __syncwarp();                      // the uniform list writes of this event are visible to every lane
+    if (ns < cs) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            const int i = c0 + lane;
+            uint16_t v = 0;
+            if (i < C) v = ab[cs + i];
+            __syncwarp();
+            if (i < C) ab[ns + i] = v;
+            __syncwarp();
+        }
+    } else {
+#pragma unroll 1
+        for (int c0 = ((C - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
+            const int i = c0 + lane;
+            uint16_t v = 0;
+            if (i < C) v = ab[cs + i];
+            __syncwarp();
+            if (i < C) ab[ns + i] = v;
+            __syncwarp();
+        }
+    }
+    return ns;
+}
+
+// up to K1_WPC warps per CTA, 4 CTAs per SM: 28 trajectories per SM at 72 registers and 8 B of shared memory per
+// particle (N = 1000); small batches run with fewer warps per CTA so that they spread over all SMs
+template <typename SnT, typename OffT, int EB>
+__global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using ST = SnTraits<SnT>;
+    using PT = PackTraits<EB>;
     constexpr int SH_A = ST::SH_A, SH_B = ST::SH_B;
     constexpr uint32_t CMASK = ST::MASK;
+    constexpr uint32_t EMPTY = PT::EMPTY;
     const int lane = threadIdx.x & 31;
+    // this lane's word and shift inside a pass of WPP words (lanes beyond EPW*WPP never hold an entry)
+    const int lw = lane < PT::EPW * PT::WPP ? lane / PT::EPW : (1 << 28);
+    const int ls = (lane % PT::EPW) * EB;
     unsigned char *slice = smem_raw + (size_t)(threadIdx.x >> 5) * (size_t)a.lay.slice;
     OffT *off = reinterpret_cast<OffT *>(slice + a.lay.o_off);
     SnT *sn = reinterpret_cast<SnT *>(slice + a.lay.o_sn);
-    uint16_t *ab = reinterpret_cast<uint16_t *>(slice + a.lay.o_ab);    // A from the front, B from the back
+    uint16_t *ab = reinterpret_cast<uint16_t *>(slice + a.lay.o_ab);    // A from the front, B from the back, C in the gap
     uint16_t *pos = reinterpret_cast<uint16_t *>(slice + a.lay.o_pos);
-    uint16_t *cl = reinterpret_cast<uint16_t *>(slice + a.lay.o_cl);
     const int N = a.N, T = a.T;
     const int NB = N - 1;                                            // B-list element k lives at ab[NB - k]
     const double tstop = a.tstop, toff = a.toff;
@@ -445,15 +533,23 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
         const PointDev pt = a.pts[slot];
         const uint32_t pidx = a.pidx[slot];
 
-        // ---- neighbour table: offsets into shared memory, entries stay in global memory
+        // ---- neighbour table: row offsets into shared memory, packed rows stay in global memory
         const uint32_t *__restrict__ goff = reinterpret_cast<const uint32_t *>((uintptr_t)rec);
-        const uint16_t *__restrict__ nbr =
-            reinterpret_cast<const uint16_t *>((uintptr_t)rec + (((size_t)(N + 1) * 4 + 15) & ~(size_t)15));
-                for (int i = lane; i <= N; i += 32) off[i] = (OffT)goff[i];
+        const uint32_t *__restrict__ words =
+            reinterpret_cast<const uint32_t *>((uintptr_t)rec + (((size_t)(N + 1) * 4 + 15) & ~(size_t)15));
+        for (int i = lane; i <= N; i += 32) off[i] = (OffT)goff[i];
         __syncwarp();
-        // ---- initial state: everything A (forward_simulator.jl:148-149)
+        // ---- initial state: everything A (forward_simulator.jl:148-149); nA = degree = valid entries of the row
         for (int i = lane; i < N; i += 32) {
-            const uint32_t deg = (uint32_t)off[i + 1] - (uint32_t)off[i];
+            const int o0 = (int)off[i], nw = (int)off[i + 1] - o0;
+            uint32_t deg = 0u;
+            if (nw > 0) {
+                // every word but the last is full; the last one holds 1..EPW entries
+                const uint32_t wl = __ldg(words + (uint32_t)(o0 + nw - 1));
+                deg = (uint32_t)(nw - 1) * PT::EPW;
+#pragma unroll
+                for (int e = 0; e < PT::EPW; ++e) deg += ((wl >> (e * EB)) & EMPTY) != EMPTY ? 1u : 0u;
+            }
             sn[i] = (SnT)(ST_A | (deg << SH_A));
             ab[i] = (uint16_t)i;
             pos[i] = (uint16_t)i;
@@ -461,6 +557,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
         __syncwarp();
 
         int cntA = N, cntB = 0, cntC = 0, nAB = 0;
+        int cs = 0;                                       // first slot of the complex list in ab
         double t = 0.0;
         double kon = pt.kon_eff;
         const double koff = pt.koff, konb = pt.konb;
@@ -569,15 +666,17 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 const int dAB = isab ? 1 : -1;
                 cntA -= dAB;
                 cntB += dAB;
+                cs = cl_make_room(ab, cs, cntC, cntA, N - cntB, lane);
                 ab[tl] = (uint16_t)m;
                 pos[m] = (uint16_t)nto;
                 const uint32_t v = sn[m];
                 nAB += dAB * ((int)((v >> SH_A) & CMASK) - (int)((v >> SH_B) & CMASK));
                 sn[m] = (SnT)((v & ~3u) | (isab ? ST_B : ST_A));       // idempotent: every lane stores the same word
                 const uint32_t dlt = (1u << SH_B) - (1u << SH_A);
-                const NbrRow rowm = load_row<OffT>(nbr, off, m, lane);
-                apply_row<false, SnT>(sn, rowm, isab ? dlt : 0u - dlt, 0, 0u, lane);
-                if (__builtin_expect(rowm.dg > 32, 0)) apply_row_tail<false, SnT>(sn, nbr, rowm, isab ? dlt : 0u - dlt, 0, 0u, lane);
+                const NbrRow rowm = load_row<OffT, EB>(words, off, m, lw, ls);
+                apply_row<false, SnT, EB>(sn, rowm, isab ? dlt : 0u - dlt, 0u, 0u);
+                if (__builtin_expect(rowm.nw > PT::WPP, 0))
+                    apply_row_tail<false, SnT, EB>(sn, words, rowm, isab ? dlt : 0u - dlt, 0u, 0u, lw, ls);
                 __syncwarp();
             } else if (x < cP) {
                 // A + B --> C (:256-289): pair number k of the nAB active pairs, enumerated along the
@@ -608,28 +707,26 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                     }
                     k -= tot;
                 }
-                // k-th neighbour of xsel in state `want`
+                // k-th neighbour of xsel in state `want`; the first pass of xsel's row stays in registers for
+                // the update below
                 int ysel = 0;
-                {
-                    const int o0 = (int)off[xsel], o1 = (int)off[xsel + 1];
-                    for (int q0 = o0; q0 < o1; q0 += 32) {
-                        const int qq = q0 + lane;
-                        int j = 0;
-                        bool ok = false;
-                        if (qq < o1) {
-                            j = ld_nbr(nbr, (uint32_t)qq);
-                            ok = ((uint32_t)sn[j] & 3u) == want;
-                        }
-                        const uint32_t bal = __ballot_sync(FULL, ok);
-                        const int c = __popc(bal);
-                        if (k < c) {
-                            // the lane holding set bit number k of the ballot
-                            const uint32_t pick = __ballot_sync(FULL, ok && __popc(bal & lanemask_lt()) == k);
-                            ysel = __shfl_sync(FULL, j, __ffs(pick) - 1);
-                            break;
-                        }
-                        k -= c;
+                NbrRow rowx;
+                rowx.o0 = (int)off[xsel];
+                rowx.nw = (int)off[xsel + 1] - rowx.o0;
+                rowx.j = EMPTY;
+                for (int w0 = 0; w0 < rowx.nw; w0 += PT::WPP) {
+                    const uint32_t j = ld_entry<EB>(words, rowx.o0, rowx.nw, w0 + lw, ls);
+                    if (w0 == 0) rowx.j = j;
+                    const bool ok = j != EMPTY && ((uint32_t)sn[j != EMPTY ? j : 0u] & 3u) == want;
+                    const uint32_t bal = __ballot_sync(FULL, ok);
+                    const int c = __popc(bal);
+                    if (k < c) {
+                        // the lane holding set bit number k of the ballot
+                        const uint32_t pick = __ballot_sync(FULL, ok && __popc(bal & lanemask_lt()) == k);
+                        ysel = (int)__shfl_sync(FULL, j, __ffs(pick) - 1);
+                        break;
                     }
+                    k -= c;
                 }
                 const int ma = sideA ? xsel : ysel;   // the A member
                 const int mb = sideA ? ysel : xsel;   // the B member
@@ -645,7 +742,8 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                     ab[NB - ib] = (uint16_t)lastB;
                     pos[lastB] = (uint16_t)ib;
                     --cntB;
-                    cl[cntC] = (uint16_t)ma;
+                    if (cntC == 0) cs = cntA;         // the gap just opened: [cntA, N - cntB) holds 2 slots
+                    ab[cs + cntC] = (uint16_t)ma;
                     pos[ma] = (uint16_t)mb;
                     pos[mb] = (uint16_t)ma;
                     ++cntC;
@@ -653,18 +751,21 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 const uint32_t va = sn[ma], vb = sn[mb];
                 // a's neighbours lose an A neighbour, and b (one of them) drops B(2) -> C(0);
                 // b's neighbours lose a B neighbour, and a drops A(1) -> C(0)
-                const NbrRow rowa = load_row<OffT>(nbr, off, ma, lane);
-                const NbrRow rowb = load_row<OffT>(nbr, off, mb, lane);
+                const NbrRow rowy = load_row<OffT, EB>(words, off, ysel, lw, ls);
+                NbrRow rowa, rowb;                  // selected by value: both stay in registers
+                rowa.o0 = sideA ? rowx.o0 : rowy.o0; rowa.nw = sideA ? rowx.nw : rowy.nw; rowa.j = sideA ? rowx.j : rowy.j;
+                rowb.o0 = sideA ? rowy.o0 : rowx.o0; rowb.nw = sideA ? rowy.nw : rowx.nw; rowb.j = sideA ? rowy.j : rowx.j;
                 nAB -= (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) - 1;
                 __syncwarp();   // every lane has read va, vb before the partner words change
-                apply_pair<SnT>(sn, nbr, rowa, rowb, 0u - (1u << SH_A), 0u - (1u << SH_B), ma, mb, 0u - 2u, 0u - 1u, lane);
+                apply_pair<SnT, EB>(sn, words, rowa, rowb, 0u - (1u << SH_A), 0u - (1u << SH_B), ma, mb, 0u - 2u, 0u - 1u, lw, ls);
             } else {
                 // C --> A + B (:291-344): complex k; the freed end is chosen by a fair coin (:300-307)
                 const int k = (int)__umulhi(vw, (uint32_t)cntC);
-                int ma = cl[k];                      // the member that was A when the complex formed
+                int ma = ab[cs + k];                 // the member that was A when the complex formed
                 int mb = pos[ma];                    // its partner
-                cl[k] = cl[cntC - 1];
+                ab[cs + k] = ab[cs + cntC - 1];
                 --cntC;
+                cs = cl_make_room(ab, cs, cntC, cntA + 1, N - cntB - 1, lane);
                 if (vw & 1u) {
                     const int tmp = ma;
                     ma = mb;
@@ -679,11 +780,11 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 5 ? 5 : 6) spr_traj_kernel(co
                 const uint32_t va = sn[ma], vb = sn[mb];
                 // a's neighbours gain an A neighbour, and b becomes B: C(0) -> B(2);
                 // b's neighbours gain a B neighbour, and a becomes A: C(0) -> A(1)
-                const NbrRow rowa = load_row<OffT>(nbr, off, ma, lane);
-                const NbrRow rowb = load_row<OffT>(nbr, off, mb, lane);
+                const NbrRow rowa = load_row<OffT, EB>(words, off, ma, lw, ls);
+                const NbrRow rowb = load_row<OffT, EB>(words, off, mb, lw, ls);
                 nAB += (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) + 1;
                 __syncwarp();
-                apply_pair<SnT>(sn, nbr, rowa, rowb, 1u << SH_A, 1u << SH_B, ma, mb, 2u, 1u, lane);
+                apply_pair<SnT, EB>(sn, words, rowa, rowb, 1u << SH_A, 1u << SH_B, ma, mb, 2u, 1u, lw, ls);
             }
             if (last) {
                 done = true;
@@ -730,14 +831,15 @@ __global__ void fixed_graph_count_kernel(const double *locs, int N, int DIM, dou
     if (maxdeg) atomicMax(maxdeg, c);
 }
 
-__global__ void fixed_graph_scan_kernel(uint32_t *deg_off, int N, unsigned long long *total) {
-    // single block; serial chunks + shared scan (N <= 65535, run once per call)
+__global__ void fixed_graph_scan_kernel(uint32_t *deg_off, int N, int epw, unsigned long long *total) {
+    // single block; serial chunks + shared scan (N <= 65535, run once per call).  In: degrees; out: exclusive
+    // offsets in WORDS of the packed rows (epw entries per word), total words in *total
     __shared__ unsigned long long part[1024];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int per = (N + nt - 1) / nt;
     const int b = tid * per, e = min(b + per, N);
     unsigned long long s = 0;
-    for (int i = b; i < e; ++i) s += deg_off[i];
+    for (int i = b; i < e; ++i) s += (deg_off[i] + (uint32_t)epw - 1u) / (uint32_t)epw;
     part[tid] = s;
     __syncthreads();
     if (tid == 0) {
@@ -753,22 +855,20 @@ __global__ void fixed_graph_scan_kernel(uint32_t *deg_off, int N, unsigned long 
     __syncthreads();
     unsigned long long run = part[tid];
     for (int i = b; i < e; ++i) {
-        const uint32_t v = deg_off[i];
+        const uint32_t v = (deg_off[i] + (uint32_t)epw - 1u) / (uint32_t)epw;
         deg_off[i] = (uint32_t)run;
         run += v;
     }
 }
 
 __global__ void fixed_graph_fill_kernel(const double *locs, int N, int DIM, double L, double reach2,
-                                        const uint32_t *off, uint16_t *nbr, long long cap) {
+                                        const uint32_t *off, uint32_t *words, int epw, int eb) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    long long w = off[i];
+    RowPacker pk{words + off[i], 0u, 0, epw, eb};
     for (int j = 0; j < N; ++j)
-        if (j != i && ref_dist_sq(locs + (size_t)i * DIM, locs + (size_t)j * DIM, DIM, L) <= reach2) {
-            if (w < cap) nbr[w] = (uint16_t)j;
-            ++w;
-        }
+        if (j != i && ref_dist_sq(locs + (size_t)i * DIM, locs + (size_t)j * DIM, DIM, L) <= reach2) pk.push((uint32_t)j);
+    pk.flush();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1002,11 +1102,11 @@ cudaError_t set_table_attr(int bytes) {
     return cudaSuccess;
 }
 
-template <typename SnT, typename OffT, int WPC>
+template <typename SnT, typename OffT, int EB>
 cudaError_t set_traj_attr(int bytes) {
     static int configured = -1;
     if (bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<SnT, OffT, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<SnT, OffT, EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
         configured = bytes;
     }
@@ -1053,32 +1153,31 @@ cudaError_t launch_table(const TableArgs &a, int DIM, int nblocks, cudaStream_t 
     return cudaGetLastError();
 }
 
-bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int smem_per_sm, TrajLayout *out, int variant) {
+bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int smem_per_sm, TrajLayout *out) {
     TrajLayout l{};
     l.wide_sn = wide_sn ? 1 : 0;
     l.wide_off = wide_off ? 1 : 0;
+    l.eb = entry_bits(N);
     int o = 0;
     l.o_off = o;  o += align16((N + 1) * (wide_off ? 4 : 2));
     l.o_sn = o;   o += align16(N * (wide_sn ? 4 : 2));
     l.o_ab = o;   o += align16(N * 2);
     l.o_pos = o;  o += align16(N * 2);
-    l.o_cl = o;   o += align16((N / 2 + 1) * 2);
     l.slice = o;
-    // warps per CTA: most resident trajectories per SM (every CTA also costs 1 KB of reserved shared memory)
+    // warps per CTA: most resident trajectories per SM (every CTA also costs 1 KB of reserved shared memory);
+    // 72 registers allow 28 warps per SM
     int best = 0, best_w = 0, best_c = 0;
-    const int wmax = variant == 4 ? 4 : 5;
-    for (int w = 1; w <= wmax; ++w) {
+    for (int w = 1; w <= K1_WPC; ++w) {
         const long long bytes = (long long)w * l.slice;
         if (bytes > smem_optin) break;
         int c = (int)(smem_per_sm / (bytes + 1024));
         if (c > 32) c = 32;
-        const int regcap = (variant == 4 ? 24 : 25) / w;   // registers: at most 24 (80 regs) or 25 (72 regs) warps per SM
+        const int regcap = K1_MAX_WARPS / w;
         if (c > regcap) c = regcap;
-        if (c * w > best) { best = c * w; best_w = w; best_c = c; }
+        if (c * w >= best && c * w > 0) { best = c * w; best_w = w; best_c = c; }
     }
     l.wpc = best_w;
     l.cta_per_sm = best_c;
-    l.variant = wmax;
     *out = l;
     return best > 0;
 }
@@ -1088,29 +1187,29 @@ cudaError_t launch_traj(const TrajArgs &a, int nblocks, cudaStream_t st) {
         using S_ = decltype(sn_t);
         using O_ = decltype(off_t);
         const int bytes = a.lay.slice * a.lay.wpc;
-        if (a.lay.variant == 4) {
-            cudaError_t e = set_traj_attr<S_, O_, 4>(bytes);
+        if (a.lay.eb == 10) {
+            cudaError_t e = set_traj_attr<S_, O_, 10>(bytes);
             if (e != cudaSuccess) return e;
-            spr_traj_kernel<S_, O_, 4><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+            spr_traj_kernel<S_, O_, 10><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
         } else {
-            cudaError_t e = set_traj_attr<S_, O_, 5>(bytes);
+            cudaError_t e = set_traj_attr<S_, O_, 16>(bytes);
             if (e != cudaSuccess) return e;
-            spr_traj_kernel<S_, O_, 5><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+            spr_traj_kernel<S_, O_, 16><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
         }
         return cudaGetLastError();
     });
 }
 
 cudaError_t launch_fixed_graph(const double *d_locs, int N, int DIM, double L, double reach, uint32_t *d_off,
-                               uint16_t *d_nbr, long long nbr_cap, unsigned long long *d_total,
-                               unsigned int *d_maxdeg, cudaStream_t st) {
+                               uint32_t *d_words, unsigned long long *d_total, unsigned int *d_maxdeg, cudaStream_t st) {
     const double reach2 = reach * reach;
     const int nb = (N + 127) / 128;
-    if (d_nbr == nullptr) {
+    const int eb = entry_bits(N), epw = entries_per_word(N);
+    if (d_words == nullptr) {
         fixed_graph_count_kernel<<<nb, 128, 0, st>>>(d_locs, N, DIM, L, reach2, d_off, d_maxdeg);
-        fixed_graph_scan_kernel<<<1, 1024, 0, st>>>(d_off, N, d_total);
+        fixed_graph_scan_kernel<<<1, 1024, 0, st>>>(d_off, N, epw, d_total);
     } else {
-        fixed_graph_fill_kernel<<<nb, 128, 0, st>>>(d_locs, N, DIM, L, reach2, d_off, d_nbr, nbr_cap);
+        fixed_graph_fill_kernel<<<nb, 128, 0, st>>>(d_locs, N, DIM, L, reach2, d_off, d_words, epw, eb);
     }
     return cudaGetLastError();
 }

@@ -15,7 +15,10 @@ struct PointDev {          // one parameter point as the kernels see it
 // : tk0 + q.  Both kernels are persistent and pull local tickets from a global counter.
 //
 // Neighbour-table record of one trajectory, written by K2 into the HBM arena and read by K1:
-//     [ off u32[N+1] | pad to 16 B | nbr u16[off[N]] | pad to 16 B ]
+//     [ off u32[N+1] | pad to 16 B | words u32[off[N]] | pad to 16 B ]
+// off[i] = first WORD of the row of particle i; a row holds its neighbours packed entries_per_word(N) to a
+// 32-bit word (10-bit entries, 3 per word, when N <= 1023; else 16-bit, 2 per word), the last word padded
+// with all-ones entries.
 // `desc[q]` holds the device address of the record of local ticket q, or 0 when the arena was full
 // (the ticket is then listed in `defer_list` and neither kernel simulates it in this launch).
 // ------------------------------------------------------------------------------------------------
@@ -41,6 +44,7 @@ struct TableArgs {                      // K2: spr_table_kernel
     long long *defer_list;              // [ntickets]
     uint16_t *stage;                    // [nblocks][N][stage_cap] staging rows of the distance pass
     int stage_cap;                      // entries per staging row (>= the stride any trajectory of the launch uses)
+    int epw, eb;                        // packed rows: entries per word, bits per entry (entries_per_word / entry_bits)
     uint64_t *spos_out;                 // test hook: packed sorted lattice positions of local ticket 0, or nullptr
 };
 
@@ -48,18 +52,25 @@ enum { OBS_TOTAL_BOUND = 0, OBS_TOTAL_A = 1, OBS_RAW_BC = 2 };
 
 // Byte offsets inside one warp's shared-memory slice of K1 (one warp = one trajectory).
 struct TrajLayout {
-    int o_off;      // OffT[N+1]   CSR offsets of the neighbour table
+    int o_off;      // OffT[N+1]   first word of every packed neighbour row
     int o_sn;       // SnT[N]      state | nA << 2 | nB << (2 + CB)
-    int o_ab;       // u16[N]      particles in state A from the front, in state B from the back
+    int o_ab;       // u16[N]      state-A particles from the front, state-B from the back, one member of every
+                    //             complex in the gap between them (A + B + 2C = N)
     int o_pos;      // u16[N]      A/B: index in its list; C: index of the partner
-    int o_cl;       // u16[N/2+1]  one member (the former A) of every complex
     int slice;      // bytes per warp
     int wide_sn;    // SnT = uint32_t (15-bit neighbour counts) instead of uint16_t (7-bit)
-    int wide_off;   // OffT = uint32_t (more than 65535 directed entries)
+    int wide_off;   // OffT = uint32_t (more than 65535 words of packed rows)
+    int eb;         // bits per packed table entry (10 or 16)
     int wpc;        // warps (trajectories) per CTA
     int cta_per_sm;
-    int variant;    // kernel instantiation: 5 (up to 5 warps per CTA, 72 registers) or 4 (4 warps, 80 registers)
 };
+
+constexpr int K1_WPC = 7;          // warps per CTA at full occupancy: 4 CTAs x 7 warps = 28 trajectories per SM
+constexpr int K1_MAX_WARPS = 28;   // 72 registers per thread
+
+// packed table entries: 10 bits (3 per word) while every particle index and the EMPTY marker fit, else 16 (2 per word)
+inline int entry_bits(int N) { return N <= 1023 ? 10 : 16; }
+inline int entries_per_word(int N) { return N <= 1023 ? 3 : 2; }
 
 struct TrajArgs {                       // K1: spr_traj_kernel
     int N, T;
@@ -100,8 +111,8 @@ struct FitArgs {                        // K5: fit_loss_kernel
 cudaError_t launch_fit_loss(const FitArgs &a, long long npop, cudaStream_t st);
 
 inline size_t align16z(size_t x) { return (x + 15) & ~(size_t)15; }
-inline size_t record_bytes(int N, unsigned long long entries) {
-    return align16z(sizeof(uint32_t) * (size_t)(N + 1)) + align16z(sizeof(uint16_t) * (size_t)entries);
+inline size_t record_bytes(int N, unsigned long long words) {
+    return align16z(sizeof(uint32_t) * (size_t)(N + 1)) + align16z(sizeof(uint32_t) * (size_t)words);
 }
 
 // K2
@@ -112,15 +123,14 @@ cudaError_t launch_table(const TableArgs &a, int DIM, int nblocks, cudaStream_t 
 constexpr int K2_THREADS = 256;
 
 // K1: picks the warps-per-CTA that keeps the most trajectories resident per SM; false if one slice does not fit
-bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int smem_per_sm, TrajLayout *out,
-                      int variant = 5);
+bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int smem_per_sm, TrajLayout *out);
 cudaError_t launch_traj(const TrajArgs &a, int nblocks, cudaStream_t st);
 
 // fixed-position neighbour table (K2b): FP64, the reference's periodic_dist_sq.
-// d_nbr == nullptr: degrees -> exclusive offsets in d_off[0..N] and the total in *d_total;
-// else: fill d_nbr (capacity nbr_cap entries) using the offsets.
+// d_words == nullptr: degrees -> exclusive word offsets of the packed rows in d_off[0..N], total words in *d_total;
+// else: fill the packed rows using the offsets.
 cudaError_t launch_fixed_graph(const double *d_locs, int N, int DIM, double L, double reach,
-                               uint32_t *d_off /* N+1 */, uint16_t *d_nbr, long long nbr_cap,
+                               uint32_t *d_off /* N+1 */, uint32_t *d_words,
                                unsigned long long *d_total, unsigned int *d_maxdeg, cudaStream_t st);
 
 // K3: replicate reduction / sequential-stop scan

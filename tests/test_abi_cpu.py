@@ -95,18 +95,18 @@ def test_merge_slice_scatter(built_lib):
 
 
 def test_shared_memory_plan(built_lib):
-    """host logic of the occupancy plan (no device): N = 1000 keeps 25 trajectories resident per SM with
-    16-bit state words, fewer with the wide instantiations; oversize N is refused"""
+    """host logic of the occupancy plan (no device): N = 1000 keeps 28 trajectories resident per SM with
+    16-bit state words (8 B of shared memory per particle), fewer with the wide instantiations; oversize N is refused"""
     from sprb200 import _lib
     slice_b, wpc, ctas, k2 = _lib.traj_layout(1000)
-    assert slice_b == 9024 and wpc * ctas == 25
+    assert slice_b == 8016 and wpc * ctas == 28
     assert wpc * slice_b <= 227 * 1024 and ctas * (wpc * slice_b + 1024) <= 228 * 1024
     assert k2 <= 227 * 1024
     s2, w2, c2, _ = _lib.traj_layout(1000, wide_state=True, wide_offsets=True)
-    assert s2 > slice_b and w2 * c2 < 25 and c2 * (w2 * s2 + 1024) <= 228 * 1024
+    assert s2 > slice_b and w2 * c2 < 28 and c2 * (w2 * s2 + 1024) <= 228 * 1024
     for n in (1, 2, 100, 5000):
         s, w, c, _ = _lib.traj_layout(n)
-        assert w >= 1 and c >= 1 and c * (w * s + 1024) <= 228 * 1024 and w * c <= 25
+        assert w >= 1 and c >= 1 and c * (w * s + 1024) <= 228 * 1024 and w * c <= 28
     with pytest.raises(_lib.SprB200Error) as e:
         _lib.traj_layout(40000)
     assert e.value.code == _lib.ERR_TOO_LARGE

@@ -288,13 +288,13 @@ def test_gpu_grid_sample_parity(engine, oracle_libs, gname):
     run = sprb200.make_run(nsims=NG, seed=BASE_SEED + 7)
     # the moments of the same streams the slice builder uses: parameter index = linear index - 1
     gm, gv, gev = [], [], []
-    for k, i in enumerate(idx):
-        m, v, n, ev = gpu_moments(engine, sim, pts[k], NG, BASE_SEED + 7, 1000, pidx=int(i) - 1)
-        gm.append(m); gv.append(v); gev.append(ev / n)
     rows, nu, nev = engine.build_indices(grid, sim, run, idx)
     assert np.all(nu == NG)
-    for k in range(len(idx)):
-        assert np.array_equal(rows[k], gm[k])                       # build == simulate, bit for bit
+    for k, i in enumerate(idx):
+        out = engine.simulate(sim, [pts[k]], sprb200.make_run(nsims=NG, seed=BASE_SEED + 7, param_index_base=int(i) - 1))
+        assert np.array_equal(rows[k], out["mean"][0])               # build == simulate, bit for bit
+        s1, s2 = out["sum"][0].astype(float), out["sumsq"][0].astype(float)
+        gm.append(out["mean"][0]); gv.append((s2 - s1 ** 2 / NG) / (NG - 1) / 1000.0 ** 2); gev.append(int(out["n_events"][0]) / NG)
     # oracle replicates per point: about 6 core-seconds each, 200..2000
     cost = np.array(gev) / 1.0e6 + 0.003                             # core-seconds per replicate (oracle: ~1e6 events/s + setup)
     nreps = np.clip((6.0 / cost).astype(int), 200, 2000)
