@@ -290,18 +290,27 @@ int spr_mirror_trajectory(const MirrorSim *sim, double kon_eff, double koff, dou
         const double cP = fma(konb, (double)nAB, cB);
         const double a0 = fma(kc, (double)cntC, cP);
         double tn = spr_mirror_next_time(t, E, a0);
-        int switched = 0;
-        if (on && tn >= toff) { tn = toff; switched = 1; }
-        if (tn > tp) {
-            while (sidx < T && tsave[sidx] < tn) {
-                curve1[sidx] = (uint16_t)(observable == 1 ? cntA : (observable == 2 ? cntB : cntB + cntC));
-                if (curve2) curve2[sidx] = (uint16_t)cntC;
-                sidx++;
+        /* specification v5: an event is "fast" (no save slot, no switch-off, not the last one) iff
+         * E < (tfast - t) a0, tfast = min(next save time, switch-off time while the bath is on, tstop);
+         * every other event takes the checks below */
+        const double tfast = fmin(fmin(tp, on ? toff : INFINITY), tstop);
+        const int fast = E < (tfast - t) * a0;
+        int lastev = 0;
+        if (!fast) {
+            int switched = 0;
+            if (on && tn >= toff) { tn = toff; switched = 1; }
+            if (tn > tp) {
+                while (sidx < T && tsave[sidx] < tn) {
+                    curve1[sidx] = (uint16_t)(observable == 1 ? cntA : (observable == 2 ? cntB : cntB + cntC));
+                    if (curve2) curve2[sidx] = (uint16_t)cntC;
+                    sidx++;
+                }
+                tp = sidx < T ? tsave[sidx] : INFINITY;
             }
-            tp = sidx < T ? tsave[sidx] : INFINITY;
+            if (switched) { t = toff; kon = 0.0; on = 0; continue; }
+            if (!(tn < INFINITY)) break;
+            lastev = tn > tstop;
         }
-        if (switched) { t = toff; kon = 0.0; on = 0; continue; }
-        if (!(tn < INFINITY)) break;
         t = tn;
         nev++;
         const double x = ((double)r[2] * 0x1.0p-32) * a0;
@@ -356,7 +365,7 @@ int spr_mirror_trajectory(const MirrorSim *sim, double kon_eff, double koff, dou
             state[ma] = ST_A; state[mb] = ST_B;
             bump(&tb, nA, ma, +1); bump(&tb, nB, mb, +1);
         }
-        if (t > tstop) break;
+        if (lastev) break;
     }
     for (int s = sidx; s < T; s++) {
         curve1[s] = (uint16_t)(observable == 1 ? cntA : (observable == 2 ? cntB : cntB + cntC));

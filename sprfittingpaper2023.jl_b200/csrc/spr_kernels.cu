@@ -468,7 +468,7 @@ __device__ __forceinline__ int scan_small(int v, int lane, int nact) {
 // [lo, hi) is the gap as it will be once the list appends of the current event are done; the block is moved
 // (rarely: it is re-aligned to the side the gap is drifting away from) only when it would collide.
 __device__ __forceinline__ int cl_make_room(uint16_t *ab, int cs, int C, int lo, int hi, int lane) {
-    if (C == 0 || (cs >= lo && cs + C <= hi)) return cs;
+    if ((unsigned)(cs - lo) <= (unsigned)(hi - C - lo) || C == 0) return cs;   // lo <= cs <= hi - C
     const int ns = cs < lo ? hi - C : lo;
     __syncwarp();                      // the uniform list writes of this event are visible to every lane
     if (ns < cs) {
@@ -605,7 +605,11 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
             // +inf (nothing can fire), which the slow path sorts out
             double tn = __dadd_rn(t, __dmul_rn(E, __drcp_rn(a0)));
 
-            if (!(tn < tfast)) {
+            // fast-path test in the multiplied form E < (tfast - t) a0 (specification v5): two operations after a0
+            // instead of the ten of the reciprocal chain, which now overlaps the event's own work (tn is first
+            // needed by the next event).  NaN/inf cases (a0 == 0, tfast == inf) fall to the slow path or behave
+            // as the quotient form does.
+            if (!(E < __dmul_rn(__dadd_rn(tfast, -t), a0))) {
                 // ---- slow path: antibody bath removed at tstop_AtoB (forward_simulator.jl:174-181,
                 // 199-202), save slots strictly before the next event keep the current state (:188-194)
                 bool switched = false;

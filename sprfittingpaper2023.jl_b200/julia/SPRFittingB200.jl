@@ -25,7 +25,7 @@ using SPRFittingPaper2023
 using SPRFittingPaper2023: BioPhysParams, SimParams, SurrogateParams, TotalBoundOutputter,
     TotalAOutputter, SimNumberTerminator, VarianceTerminator, getdim
 import SPRFittingPaper2023: isnotdone, update!, reset!
-using OnlineStats: Variance, Mean
+using OnlineStats: Variance, Mean, nobs, merge!
 using StaticArrays: SVector
 using Random: rand, RandomDevice
 
@@ -117,7 +117,10 @@ function run_spr_sim!(outputter, biopars::BioPhysParams, simpars::SimParams,
     T = length(simpars.tsave)
     builtin_out = outputter isa TotalBoundOutputter || outputter isa TotalAOutputter
     builtin_term = terminator isa SimNumberTerminator || terminator isa VarianceTerminator
-    if builtin_out && builtin_term
+    # the on-device VarianceTerminator scans replicates from the first one: an outputter that already holds
+    # replicates (the reference keeps accumulating into it, forward_simulator.jl:357) takes the replay path
+    fresh = builtin_out && nobs(first(outputter.bindcnt)) == 0
+    if builtin_out && builtin_term && (fresh || terminator isa SimNumberTerminator)
         obs = outputter isa TotalAOutputter ? OBS_TOTAL_A : OBS_TOTAL_BOUND
         run = if terminator isa SimNumberTerminator
             todo = simpars.nsims - terminator.num_completed_sims
@@ -139,10 +142,12 @@ function run_spr_sim!(outputter, biopars::BioPhysParams, simpars::SimParams,
             end
         end
         n = Int(nused[1]); scale = biopars.CP / simpars.N
+        # accumulate INTO the outputter's running statistics, as the per-replicate fit! of the reference does
+        # (forward_simulator.jl:357, callbacks.jl:27-30): OnlineStats merges two Variance/Mean states exactly
         for i in 1:T
-            outputter.bindcnt[i] = outputter isa TotalAOutputter ?
-                mean_from_moments(n, Float64(S[i]), scale) :
-                variance_from_moments(n, Float64(S[i]), Float64(Q[i]), scale)
+            merge!(outputter.bindcnt[i], outputter isa TotalAOutputter ?
+                   mean_from_moments(n, Float64(S[i]), scale) :
+                   variance_from_moments(n, Float64(S[i]), Float64(Q[i]), scale))
         end
         terminator isa SimNumberTerminator ? (terminator.num_completed_sims += n) : (terminator.notdone = false)
         outputter(biopars, simpars)
@@ -196,12 +201,25 @@ end
 
 "`build_surrogate_serial` (surrogate.jl:203-242): returns the (nkon,nkoff,nkonb,nreach,ntime) array."
 function build_surrogate_serial(surrogate_size::Tuple, surpars::SurrogateParams, simpars::SimParams;
-                                terminator=VarianceTerminator(), device=0, seed=nothing)
+                                terminator=VarianceTerminator(), device=0, devices=nothing, seed=nothing)
     @assert surrogate_size[end] == length(simpars.tsave)
-    h = handle(device)
     key = seed === nothing ? nextseed() : UInt64(seed)
     table = zeros(surrogate_size)              # column-major: exactly the library's [T][P] layout
     g = grid(surpars, surrogate_size[1:4])
+    if devices !== nothing && length(devices) > 1
+        # every listed GPU of this process takes a cost-balanced share; same bytes as one GPU
+        devs = Int32.(collect(devices))
+        with_sim(simpars) do sim
+            GC.@preserve table devs begin
+                rc = ccall((:sprb200_build_table_multi, LIB), Cint,
+                    (Ptr{Int32}, Int32, Ref{SprGrid}, Ref{SprSim}, Ref{SprRun}, Ptr{Cdouble}, Ptr{Int32}, Ptr{UInt64}),
+                    devs, length(devs), g, sim, runspec(terminator, simpars, key), table, C_NULL, C_NULL)
+                rc == 0 || error("sprb200 error $rc: " * unsafe_string(ccall((:sprb200_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+            end
+        end
+        return table
+    end
+    h = handle(devices === nothing ? device : first(devices))
     with_sim(simpars) do sim
         GC.@preserve table check(h, ccall((:sprb200_build_table, LIB), Cint,
             (Ptr{Cvoid}, Ref{SprGrid}, Ref{SprSim}, Ref{SprRun}, Ptr{Cdouble}, Ptr{Int32}, Ptr{UInt64}),
