@@ -509,7 +509,12 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
     // this lane's word and shift inside a pass of WPP words (lanes beyond EPW*WPP never hold an entry)
     const int lw = lane < PT::EPW * PT::WPP ? lane / PT::EPW : (1 << 28);
     const int ls = (lane % PT::EPW) * EB;
-    unsigned char *slice = smem_raw + (size_t)(threadIdx.x >> 5) * (size_t)a.lay.slice;
+    // The warp's slice of shared memory.  The warp index goes through a shuffle so that ptxas sees a warp-UNIFORM
+    // base address: every load of trajectory state at a uniform index is then uniform too, the data-dependent
+    // branches below become uniform branches, and the shuffles / votes / __syncwarp inside them need no
+    // convergence check (with threadIdx.x >> 5 used directly the same source compiles to 25 BRA.DIV checks, 64
+    // BSSY/BSYNC pairs and 27 % more instructions).
+    unsigned char *slice = smem_raw + (size_t)__shfl_sync(FULL, threadIdx.x >> 5, 0) * (size_t)a.lay.slice;
     OffT *off = reinterpret_cast<OffT *>(slice + a.lay.o_off);
     SnT *sn = reinterpret_cast<SnT *>(slice + a.lay.o_sn);
     uint16_t *ab = reinterpret_cast<uint16_t *>(slice + a.lay.o_ab);    // A from the front, B from the back, C in the gap
@@ -609,7 +614,11 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
             // instead of the ten of the reciprocal chain, which now overlaps the event's own work (tn is first
             // needed by the next event).  NaN/inf cases (a0 == 0, tfast == inf) fall to the slow path or behave
             // as the quotient form does.
+#ifdef SPR_FAST_V4
+            if (!(tn < tfast)) {
+#else
             if (!(E < __dmul_rn(__dadd_rn(tfast, -t), a0))) {
+#endif
                 // ---- slow path: antibody bath removed at tstop_AtoB (forward_simulator.jl:174-181,
                 // 199-202), save slots strictly before the next event keep the current state (:188-194)
                 bool switched = false;

@@ -303,8 +303,10 @@ def test_gpu_grid_sample_parity(engine, oracle_libs, gname):
     for k in range(len(idx)):
         rm, rv, rn, _ = ref[k]
         se2 = gv[k] / NG + rv / rn
-        ok = se2 > 0
-        assert np.all(gm[k][~ok] == rm[~ok])
+        assert np.all(gm[k][se2 == 0] == rm[se2 == 0])
+        # the z statistic is Gaussian only where both samples hold enough bound particles in total (the grid
+        # reaches kon' = 1e-5: a handful of binding events per thousand replicates): >= 50 counts on either side
+        ok = (se2 > 0) & (gm[k] * 1000.0 * NG >= 50.0) & (rm * 1000.0 * rn >= 50.0)
         z = (gm[k] - rm)[ok] / np.sqrt(se2[ok])
         allz.append(z)
         pmax.append(float(np.abs(z).max()) if len(z) else 0.0)
@@ -360,8 +362,12 @@ def test_gpu_grid_sample_variance_terminator(engine, oracle_libs, gname):
         from scipy.stats import spearmanr
         assert spearmanr(nu[mid], rn[mid]).statistic > 0.8
     # the means of those adaptive samples agree as well (SE from the oracle's own variance estimate)
+    # (a Gaussian bound needs enough replicates for the variance estimate and enough counts per bin: points that
+    # stop near minsims = 15 are Student-t with ~14 degrees of freedom, bound 9 instead of 5)
     for k in range(len(idx)):
         se2 = ref[k]["var"] / rn[k] * (1.0 + rn[k] / max(nu[k], 1))
-        ok = se2 > 0
+        ok = (se2 > 0) & (ref[k]["mean"] * 1000.0 * rn[k] >= 50.0) & (rows[k] * 1000.0 * nu[k] >= 50.0)
+        if not ok.any():
+            continue
         z = (rows[k] - ref[k]["mean"])[ok] / np.sqrt(se2[ok])
-        assert np.abs(z).max() < 5.0, (k, idx[k], np.abs(z).max())
+        assert np.abs(z).max() < (5.0 if min(nu[k], rn[k]) >= 100 else 9.0), (k, idx[k], np.abs(z).max())
