@@ -290,11 +290,10 @@ int spr_mirror_trajectory(const MirrorSim *sim, double kon_eff, double koff, dou
         const double cP = fma(konb, (double)nAB, cB);
         const double a0 = fma(kc, (double)cntC, cP);
         double tn = spr_mirror_next_time(t, E, a0);
-        /* specification v5: an event is "fast" (no save slot, no switch-off, not the last one) iff
-         * E < (tfast - t) a0, tfast = min(next save time, switch-off time while the bath is on, tstop);
-         * every other event takes the checks below */
+        /* an event strictly before tfast = min(next save time, switch-off time while the bath is on, tstop) needs no
+         * save-slot write, no switch-off and is not the last one; every other event takes the checks below */
         const double tfast = fmin(fmin(tp, on ? toff : INFINITY), tstop);
-        const int fast = E < (tfast - t) * a0;
+        const int fast = tn < tfast;
         int lastev = 0;
         if (!fast) {
             int switched = 0;

@@ -610,15 +610,9 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
             // +inf (nothing can fire), which the slow path sorts out
             double tn = __dadd_rn(t, __dmul_rn(E, __drcp_rn(a0)));
 
-            // fast-path test in the multiplied form E < (tfast - t) a0 (specification v5): two operations after a0
-            // instead of the ten of the reciprocal chain, which now overlaps the event's own work (tn is first
-            // needed by the next event).  NaN/inf cases (a0 == 0, tfast == inf) fall to the slow path or behave
-            // as the quotient form does.
-#ifdef SPR_FAST_V4
+            // (a fast-path test in the multiplied form E < (tfast - t) a0 takes the reciprocal chain off the critical
+            // path but costs three instructions: measured 1 % slower, profiles/r2_k1_variants.txt)
             if (!(tn < tfast)) {
-#else
-            if (!(E < __dmul_rn(__dadd_rn(tfast, -t), a0))) {
-#endif
                 // ---- slow path: antibody bath removed at tstop_AtoB (forward_simulator.jl:174-181,
                 // 199-202), save slots strictly before the next event keep the current state (:188-194)
                 bool switched = false;
