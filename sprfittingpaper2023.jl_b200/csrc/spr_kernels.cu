@@ -466,9 +466,11 @@ __device__ __forceinline__ int scan_small(int v, int lane, int nact) {
 
 // The complex list lives in ab[cs .. cs+C), inside the gap between the A list (front) and the B list (back).
 // [lo, hi) is the gap as it will be once the list appends of the current event are done; the block is moved
-// (rarely: it is re-aligned to the side the gap is drifting away from) only when it would collide.
-__device__ __forceinline__ int cl_make_room(uint16_t *ab, int cs, int C, int lo, int hi, int lane) {
-    if ((unsigned)(cs - lo) <= (unsigned)(hi - C - lo) || C == 0) return cs;   // lo <= cs <= hi - C
+// (rarely: it is re-aligned to the side the gap is drifting away from) only when it would collide -- the callers
+// test the one side that can collide before calling.
+__device__ __noinline__ int cl_make_room(uint16_t *ab, int cs, int C, int lo, int hi, int lane) {
+    if (C == 0) return lo;
+    if (cs >= lo && cs + C <= hi) return cs;
     const int ns = cs < lo ? hi - C : lo;
     __syncwarp();                      // the uniform list writes of this event are visible to every lane
     if (ns < cs) {
@@ -568,13 +570,12 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
         const double koff = pt.koff, konb = pt.konb;
         const double kc = __dmul_rn(2.0, koff);           // C -> A+B rate (forward_simulator.jl:135)
         bool on = true;
-        bool last = false;
         int sidx = 0;
         double tp = tsave[0];
         // fast-path deadline: an event strictly before it needs no save-slot write, no switch-off and is
         // not the last one
         double tfast = fmin(fmin(tp, toff), tstop);
-        uint32_t ndraw = 0, nskip = 0;
+        uint32_t ndraw = 0, nskip = 0;                     // draws of the finished 32-blocks; draws that fired no event
         const size_t row = (size_t)slot * a.repstride + (size_t)(rep - a.rep_rowbase);
         uint16_t *crow = a.curve + row * (size_t)T;
         uint16_t *crow2 = a.curve2 ? a.curve2 + row * (size_t)T : nullptr;
@@ -599,7 +600,6 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
             const double E = __hiloint2double((int)__shfl_sync(FULL, rEh, src), (int)__shfl_sync(FULL, rEl, src));
             const uint32_t vz = __shfl_sync(FULL, rz, src);
             const uint32_t vw = __shfl_sync(FULL, rw, src);
-            ++ndraw;
 
             // ---- total propensity (exact integer counts x rates)
             const double cA = __dmul_rn(kon, (double)cntA);
@@ -647,10 +647,15 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
                 if (!(tn < INF)) {   // nothing can fire any more; all slots are filled
                     ++nskip;
                     done = true;
+                    ndraw += (uint32_t)src + 1u - 32u;   // the block is left after draw src (the loop's tail adds 32)
                     src = 32;        // leaves the draw loop through its own condition (single-exit loop)
                     continue;
                 }
-                last = tn > tstop;   // the first event past tstop is still applied (:173, 183)
+                if (tn > tstop) {    // the first event past tstop is still applied (:173, 183) and is the last one:
+                    done = true;     // it is applied below, then the draw loop ends through its own condition
+                    ndraw += (uint32_t)src + 1u - 32u;
+                    src = 31;
+                }
                 tfast = fmin(fmin(tp, on ? toff : INF), tstop);
             }
             t = tn;
@@ -673,7 +678,8 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
                 const int dAB = isab ? 1 : -1;
                 cntA -= dAB;
                 cntB += dAB;
-                cs = cl_make_room(ab, cs, cntC, cntA, N - cntB, lane);
+                // the gap moved one slot towards the list that shrank: only the complex block's far end can collide
+                if (isab ? cs + cntC > N - cntB : cs < cntA) cs = cl_make_room(ab, cs, cntC, cntA, N - cntB, lane);
                 ab[tl] = (uint16_t)m;
                 pos[m] = (uint16_t)nto;
                 const uint32_t v = sn[m];
@@ -772,7 +778,7 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
                 int mb = pos[ma];                    // its partner
                 ab[cs + k] = ab[cs + cntC - 1];
                 --cntC;
-                cs = cl_make_room(ab, cs, cntC, cntA + 1, N - cntB - 1, lane);
+                if (cs <= cntA || cs + cntC >= N - cntB) cs = cl_make_room(ab, cs, cntC, cntA + 1, N - cntB - 1, lane);
                 if (vw & 1u) {
                     const int tmp = ma;
                     ma = mb;
@@ -793,11 +799,8 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
                 __syncwarp();
                 apply_pair<SnT, EB>(sn, words, rowa, rowb, 1u << SH_A, 1u << SH_B, ma, mb, 2u, 1u, lw, ls);
             }
-            if (last) {
-                done = true;
-                src = 32;
-            }
           }
+          ndraw += 32u;
         }
         // ---- remaining save slots take the final state (forward_simulator.jl:349-354)
         {
