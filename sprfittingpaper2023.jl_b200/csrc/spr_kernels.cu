@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
                 cntA -= dAB;
                 cntB += dAB;
                 // the gap moved one slot towards the list that shrank: only the complex block's far end can collide
-                if (isab ? cs + cntC > N - cntB : cs < cntA) cs = cl_make_room(ab, cs, cntC, cntA, N - cntB, lane);
+                if (cntC != 0 && (isab ? cs + cntC > N - cntB : cs < cntA)) cs = cl_make_room(ab, cs, cntC, cntA, N - cntB, lane);
                 ab[tl] = (uint16_t)m;
                 pos[m] = (uint16_t)nto;
                 const uint32_t v = sn[m];
@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
                 int mb = pos[ma];                    // its partner
                 ab[cs + k] = ab[cs + cntC - 1];
                 --cntC;
-                if (cs <= cntA || cs + cntC >= N - cntB) cs = cl_make_room(ab, cs, cntC, cntA + 1, N - cntB - 1, lane);
+                if (cntC != 0 && (cs <= cntA || cs + cntC >= N - cntB)) cs = cl_make_room(ab, cs, cntC, cntA + 1, N - cntB - 1, lane);
                 if (vw & 1u) {
                     const int tmp = ma;
                     ma = mb;
