@@ -253,7 +253,8 @@ int sprb200_comm_destroy(sprb200_handle h);
 /* build_surrogate_serial across the communicator (collective: every rank calls it with the same arguments).
  * Each rank simulates its share (sprb200_deal_indices), one ncclAllGather assembles the slabs on every
  * rank and the table is permuted on the device into FirstMoment order.  out_table (host, P*T doubles) and
- * d_table (device, P*T doubles) may each be NULL; n_used / n_events: [P] host or NULL.  With nranks == 1
+ * d_table (device, P*T doubles) may each be NULL; n_used / n_events: [P] host or NULL (the output pointers may
+ * differ between ranks: the collectives issued do not depend on them).  With nranks == 1
  * no communicator is needed.  sprb200_last_stats / sprb200_last_kernel_ms report this rank's share. */
 int sprb200_build_table_dist(sprb200_handle h, const SprGrid *grid, const SprSim *sim, const SprRun *run,
                              double *out_table, double *d_table, int32_t *n_used, uint64_t *n_events);

@@ -1447,17 +1447,15 @@ int sprb200_build_table_dist(sprb200_handle h, const SprGrid *grid, const SprSim
         NCCL_TRY(h, g_nccl.AllGather(h->table.p, h->mrows.p, sizeof(double) * (size_t)maxcount * T, 0 /* ncclInt8 */,
                                      h->nccl_comm, s0));
         d_rows_all = h->mrows.as<double>();
-        if (n_used) {
-            CUDA_TRY(h, h->gnused.ensure(sizeof(int32_t) * (size_t)maxcount * nr));
-            NCCL_TRY(h, g_nccl.AllGather(h->mnused.p, h->gnused.p, sizeof(int32_t) * (size_t)maxcount, 0, h->nccl_comm, s0));
-            d_nu_all = h->gnused.as<int32_t>();
-        }
-        if (n_events) {
-            CUDA_TRY(h, h->gnev.ensure(sizeof(uint64_t) * (size_t)maxcount * nr));
-            NCCL_TRY(h, g_nccl.AllGather(h->mnev.p, h->gnev.p, sizeof(uint64_t) * (size_t)maxcount, 0, h->nccl_comm, s0));
-            d_nev_all = h->gnev.as<uint64_t>();
-        }
-        h->st_launches += 1;
+        // the replicate and event counts are gathered on EVERY rank whatever outputs it asked for: the sequence of
+        // collectives must not depend on per-rank arguments (12 bytes per point)
+        CUDA_TRY(h, h->gnused.ensure(sizeof(int32_t) * (size_t)maxcount * nr));
+        NCCL_TRY(h, g_nccl.AllGather(h->mnused.p, h->gnused.p, sizeof(int32_t) * (size_t)maxcount, 0, h->nccl_comm, s0));
+        d_nu_all = h->gnused.as<int32_t>();
+        CUDA_TRY(h, h->gnev.ensure(sizeof(uint64_t) * (size_t)maxcount * nr));
+        NCCL_TRY(h, g_nccl.AllGather(h->mnev.p, h->gnev.p, sizeof(uint64_t) * (size_t)maxcount, 0, h->nccl_comm, s0));
+        d_nev_all = h->gnev.as<uint64_t>();
+        h->st_launches += 3;
     }
     // gathered rows -> FirstMoment order (padding rows carry index 0 and are skipped)
     std::vector<int64_t> idx_all((size_t)maxcount * nr, 0);
