@@ -312,7 +312,8 @@ def main():
     if world > 1:
         # (with NCCL_DEBUG=VERSION in the environment NCCL prints its version banner to stdout at init; the JSON
         # line below is always the LAST line of rank 0's stdout)
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     eng = sprb200.Engine(local_rank)
     # the library's own communicator: rank 0 creates the id, torch.distributed only carries the 128 bytes
     uid = torch.zeros(128, dtype=torch.uint8, device=dev)
