@@ -226,10 +226,12 @@ int sprb200_scatter_rows_device(sprb200_handle h, const double *d_rows, const in
  * its random stream is keyed by (seed, linear index - 1, replicate): the table is byte-identical for
  * any number of GPUs.  The grid points are dealt to the GPUs in snake order of the a-priori cost estimate
  * (equal cost mix and equal counts per GPU). ------------------------------------------------------- */
-/* The 1-based linear indices `rank` of `nranks` simulates (ascending).  Device-free.  Writes at most `cap`
- * indices to idx_out (may be NULL) and returns the count, or a negative error. */
-int64_t sprb200_deal_indices(const SprGrid *grid, const SprSim *sim, int32_t nranks, int32_t rank,
-                             int64_t *idx_out, int64_t cap);
+/* The 1-based linear indices `rank` of `nranks` simulates (ascending).  Device-free.  `run` (may be NULL = FIXED)
+ * only matters for the VarianceTerminator, whose expected replicate count per point (15 ... 250 with the defaults)
+ * enters the cost.  Writes at most `cap` indices to idx_out (may be NULL) and returns the count, or a negative
+ * error. */
+int64_t sprb200_deal_indices(const SprGrid *grid, const SprSim *sim, const SprRun *run, int32_t nranks,
+                             int32_t rank, int64_t *idx_out, int64_t cap);
 /* build_surrogate_serial on ndev GPUs of THIS process: one host thread and one context per device (created
  * on first use, kept until sprb200_multi_release), every device simulates its share, the slabs are
  * gathered on devices[0] with peer copies (NVLink), permuted there into FirstMoment order and copied

@@ -78,7 +78,7 @@ if rank == 0:
     rng = np.random.default_rng(3)
     ok = True
     for r in range(world):
-        share = _lib.deal_indices(grid, sim, world, r)
+        share = _lib.deal_indices(grid, sim, world, r, run)
         i = int(rng.choice(share))
         pt = _lib.grid_points(grid, [i])
         r1 = _lib.make_run(variance=(0.01, 15, 250), seed=20231, param_index_base=i - 1) if variance else \

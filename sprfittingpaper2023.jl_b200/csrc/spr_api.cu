@@ -691,14 +691,44 @@ std::vector<int64_t> strided(int64_t idxstart, int64_t stride, int64_t count) {
 // order 0..w-1, w-1..0, ...: every rank simulates the same mix of cheap and expensive points and the
 // counts differ by at most one.  Deterministic and device-free: every rank computes the same lists.
 // The reference's own split is by contiguous index ranges (examples/cluster_scripts/queue_job.sh:7-17).
-int deal_points(const SprGrid *grid, const SprSim *sim, int nranks, std::vector<std::vector<int64_t>> *out) {
+// Replicates the VarianceTerminator is expected to use at a point: the stopping rule needs SEM <= ssetol * mean in
+// every bin, and the hardest bin is the one with the fewest bound particles c (relative spread of one replicate
+// 1/sqrt(c)): n = 1 / (ssetol^2 c), clamped to [minsims, maxsims].  c is taken at the first save time after 0
+// (association just started) and at tstop (dissociation, slowed by the fraction of antibodies held by both arms);
+// on 48 sampled points of the C2 and C3 grids this reproduces the measured count at 47
+// (tests/test_gpu_parity.py prints them).  Only the relative cost of the points matters here.
+double replicate_estimate(const PointDev &p, int DIM, const SprSim *sim, const SprRun *run) {
+    if (!run || run->term_kind != SPRB200_TERM_VARIANCE) return 1.0;
+    const double PI = 3.14159265358979323846;
+    const int N = sim->N;
+    double t1 = sim->tstop / 600.0;
+    if (sim->tsave)
+        for (int s = 0; s < sim->T; ++s)
+            if (sim->tsave[s] > 0.0) { t1 = sim->tsave[s]; break; }
+    const double toff = std::min(std::max(sim->tstop_AtoB, 0.0), sim->tstop);
+    const double kon = p.kon_eff, koff = p.koff, konb = p.konb;
+    const double c1 = (double)N * -std::expm1(-kon * std::min(t1, toff));
+    double frac = DIM == 3 ? (4.0 / 3.0) * PI * p.reach * p.reach * p.reach / (sim->L * sim->L * sim->L)
+                           : PI * p.reach * p.reach / (sim->L * sim->L);
+    const double dmin = std::min(1.0, (double)(N - 1) * std::min(frac, 1.0));
+    const double ptoff = (kon + koff) > 0.0 ? kon / (kon + koff) * -std::expm1(-(kon + koff) * toff) : 0.0;
+    const double fC = (konb * dmin + 2.0 * koff) > 0.0 ? konb * dmin / (konb * dmin + 2.0 * koff) : 0.0;
+    const double cend = (double)N * ptoff * std::exp(-koff * (1.0 - fC) * (sim->tstop - toff));
+    const double c = std::min(c1, cend);
+    const double tol2 = std::max(run->ssetol * run->ssetol, 1e-300);
+    const double n = c > 0.0 ? 1.0 / (tol2 * c) : (double)run->maxsims;
+    return std::min((double)run->maxsims, std::max((double)run->minsims, n));
+}
+
+int deal_points(const SprGrid *grid, const SprSim *sim, const SprRun *run, int nranks, std::vector<std::vector<int64_t>> *out) {
     int64_t P = 0;
     if (grid_total(grid, &P) || nranks < 1) return SPRB200_ERR_BAD_ARG;
     std::vector<std::pair<double, int64_t>> keyed((size_t)P);
     for (int64_t i = 0; i < P; ++i) {
         PointDev p;
         grid_point(grid, i, &p);
-        keyed[(size_t)i] = std::make_pair(-cost_estimate(p, sim->N, sim->DIM, sim->L, sim->tstop, sim->tstop_AtoB), i);
+        keyed[(size_t)i] = std::make_pair(-cost_estimate(p, sim->N, sim->DIM, sim->L, sim->tstop, sim->tstop_AtoB) *
+                                              replicate_estimate(p, sim->DIM, sim, run), i);
     }
     std::sort(keyed.begin(), keyed.end());
     out->assign((size_t)nranks, std::vector<int64_t>());
@@ -1234,13 +1264,13 @@ int sprb200_scatter_table_device(sprb200_handle h, const double *d_rows, int64_t
 }
 
 // ---- multi-GPU -------------------------------------------------------------------------------------
-int64_t sprb200_deal_indices(const SprGrid *grid, const SprSim *sim, int32_t nranks, int32_t rank, int64_t *idx_out,
-                             int64_t cap) {
+int64_t sprb200_deal_indices(const SprGrid *grid, const SprSim *sim, const SprRun *run, int32_t nranks, int32_t rank,
+                             int64_t *idx_out, int64_t cap) {
     if (!grid || !sim || nranks < 1 || rank < 0 || rank >= nranks || sim->N < 1 || (sim->DIM != 2 && sim->DIM != 3) ||
         !(sim->L > 0.0))
         return SPRB200_ERR_BAD_ARG;
     std::vector<std::vector<int64_t>> deal;
-    if (deal_points(grid, sim, nranks, &deal)) return SPRB200_ERR_BAD_ARG;
+    if (deal_points(grid, sim, run, nranks, &deal)) return SPRB200_ERR_BAD_ARG;
     const std::vector<int64_t> &mine = deal[(size_t)rank];
     if (idx_out)
         for (size_t k = 0; k < mine.size() && (int64_t)k < cap; ++k) idx_out[k] = mine[k];
@@ -1269,7 +1299,7 @@ int sprb200_build_table_multi(const int32_t *devices, int32_t ndev, const SprGri
         hs[(size_t)r] = it->second;
     }
     std::vector<std::vector<int64_t>> deal;
-    if (deal_points(grid, sim, ndev, &deal)) return fail(nullptr, SPRB200_ERR_BAD_ARG, "bad grid");
+    if (deal_points(grid, sim, run, ndev, &deal)) return fail(nullptr, SPRB200_ERR_BAD_ARG, "bad grid");
     const int T = sim->T;
     sprb200_ctx *h0 = hs[0];
     // the gathered slabs and the table live on the first device; every other device sends its slab with
@@ -1418,7 +1448,7 @@ int sprb200_build_table_dist(sprb200_handle h, const SprGrid *grid, const SprSim
     if (nr > 1 && !h->nccl_comm) return fail(h, SPRB200_ERR_BAD_ARG, "no communicator (sprb200_comm_init)");
     if (P < nr) return fail(h, SPRB200_ERR_BAD_ARG, "fewer grid points than ranks");
     std::vector<std::vector<int64_t>> deal;
-    if (deal_points(grid, sim, nr, &deal)) return fail(h, SPRB200_ERR_BAD_ARG, "bad grid");
+    if (deal_points(grid, sim, run, nr, &deal)) return fail(h, SPRB200_ERR_BAD_ARG, "bad grid");
     const int T = sim->T;
     const std::vector<int64_t> &mine = deal[(size_t)me];
     const int64_t count = (int64_t)mine.size();

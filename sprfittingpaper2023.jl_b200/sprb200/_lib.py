@@ -127,7 +127,7 @@ def load():
     L.sprb200_fit_loss.restype = C.c_int
     L.sprb200_fit_loss.argtypes = [vp, P(SprAligned), P(dbl), i64, P(dbl)]
     L.sprb200_deal_indices.restype = i64
-    L.sprb200_deal_indices.argtypes = [P(SprGrid), P(SprSim), i32, i32, P(i64), i64]
+    L.sprb200_deal_indices.argtypes = [P(SprGrid), P(SprSim), P(SprRun), i32, i32, P(i64), i64]
     L.sprb200_build_table_multi.restype = C.c_int
     L.sprb200_build_table_multi.argtypes = [P(i32), i32, P(SprGrid), P(SprSim), P(SprRun), P(dbl), P(i32), P(u64)]
     L.sprb200_multi_stats.restype = C.c_int
@@ -176,15 +176,17 @@ def grid_points(grid, idx=None):
     return out
 
 
-def deal_indices(grid, sim, nranks, rank):
+def deal_indices(grid, sim, nranks, rank, run=None):
     """1-based linear grid indices (ascending) that `rank` of `nranks` simulates: the library's own
-    cost-balanced deal (sprb200_deal_indices), the one sprb200_build_table_multi / _dist use."""
+    cost-balanced deal (sprb200_deal_indices), the one sprb200_build_table_multi / _dist use.  `run` matters for
+    the VarianceTerminator only (expected replicates per point enter the cost)."""
     L = load()
-    n = L.sprb200_deal_indices(C.byref(grid), C.byref(sim.c), nranks, rank, None, 0)
+    rp = C.byref(run) if run is not None else None
+    n = L.sprb200_deal_indices(C.byref(grid), C.byref(sim.c), rp, nranks, rank, None, 0)
     if n < 0:
         raise SprB200Error(int(n), "bad arguments to sprb200_deal_indices")
     out = np.zeros(int(n), dtype=np.int64)
-    L.sprb200_deal_indices(C.byref(grid), C.byref(sim.c), nranks, rank, _ptr(out, C.c_int64), n)
+    L.sprb200_deal_indices(C.byref(grid), C.byref(sim.c), rp, nranks, rank, _ptr(out, C.c_int64), n)
     return out
 
 
