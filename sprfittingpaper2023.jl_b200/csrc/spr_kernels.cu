@@ -434,12 +434,13 @@ __device__ __forceinline__ void apply_row_tail(SnT *sn, const uint32_t *__restri
 // by __syncwarp(), so the order of the additions is immaterial; ONE uniform branch covers both tails
 template <typename SnT, int EB>
 __device__ __forceinline__ void apply_pair(SnT *sn, const uint32_t *__restrict__ words, const NbrRow &ra, const NbrRow &rb,
-                                           uint32_t da, uint32_t db, int ma, int mb, uint32_t ea, uint32_t eb, int lw, int ls) {
+                                           uint32_t da, uint32_t db, int ma, int mb, uint32_t ea, uint32_t eb, int lw, int ls,
+                                           bool tails) {
     apply_row<true, SnT, EB>(sn, ra, da, (uint32_t)mb, ea);
     __syncwarp();
     apply_row<true, SnT, EB>(sn, rb, db, (uint32_t)ma, eb);
     __syncwarp();
-    if (__builtin_expect(max(ra.nw, rb.nw) > PackTraits<EB>::WPP, 0)) {
+    if (tails && max(ra.nw, rb.nw) > PackTraits<EB>::WPP) {
         apply_row_tail<true, SnT, EB>(sn, words, ra, da, (uint32_t)mb, ea, lw, ls);
         __syncwarp();
         apply_row_tail<true, SnT, EB>(sn, words, rb, db, (uint32_t)ma, eb, lw, ls);
@@ -547,8 +548,10 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
         for (int i = lane; i <= N; i += 32) off[i] = (OffT)goff[i];
         __syncwarp();
         // ---- initial state: everything A (forward_simulator.jl:148-149); nA = degree = valid entries of the row
+        int maxnw = 0;
         for (int i = lane; i < N; i += 32) {
             const int o0 = (int)off[i], nw = (int)off[i + 1] - o0;
+            maxnw = max(maxnw, nw);
             uint32_t deg = 0u;
             if (nw > 0) {
                 // every word but the last is full; the last one holds 1..EPW entries
@@ -562,6 +565,9 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
             pos[i] = (uint16_t)i;
         }
         __syncwarp();
+        // rows longer than one pass (more than 30 resp. 32 neighbours) exist in few trajectories: one uniform flag
+        // instead of a degree test per event
+        const bool tails = __reduce_max_sync(FULL, maxnw) > PT::WPP;
 
         int cntA = N, cntB = 0, cntC = 0, nAB = 0;
         int cs = 0;                                       // first slot of the complex list in ab
@@ -688,7 +694,7 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
                 const uint32_t dlt = (1u << SH_B) - (1u << SH_A);
                 const NbrRow rowm = load_row<OffT, EB>(words, off, m, lw, ls);
                 apply_row<false, SnT, EB>(sn, rowm, isab ? dlt : 0u - dlt, 0u, 0u);
-                if (__builtin_expect(rowm.nw > PT::WPP, 0))
+                if (tails && rowm.nw > PT::WPP)
                     apply_row_tail<false, SnT, EB>(sn, words, rowm, isab ? dlt : 0u - dlt, 0u, 0u, lw, ls);
                 __syncwarp();
             } else if (x < cP) {
@@ -770,7 +776,7 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
                 rowb.o0 = sideA ? rowy.o0 : rowx.o0; rowb.nw = sideA ? rowy.nw : rowx.nw; rowb.j = sideA ? rowy.j : rowx.j;
                 nAB -= (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) - 1;
                 __syncwarp();   // every lane has read va, vb before the partner words change
-                apply_pair<SnT, EB>(sn, words, rowa, rowb, 0u - (1u << SH_A), 0u - (1u << SH_B), ma, mb, 0u - 2u, 0u - 1u, lw, ls);
+                apply_pair<SnT, EB>(sn, words, rowa, rowb, 0u - (1u << SH_A), 0u - (1u << SH_B), ma, mb, 0u - 2u, 0u - 1u, lw, ls, tails);
             } else {
                 // C --> A + B (:291-344): complex k; the freed end is chosen by a fair coin (:300-307)
                 const int k = (int)__umulhi(vw, (uint32_t)cntC);
@@ -797,7 +803,7 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
                 const NbrRow rowb = load_row<OffT, EB>(words, off, mb, lw, ls);
                 nAB += (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) + 1;
                 __syncwarp();
-                apply_pair<SnT, EB>(sn, words, rowa, rowb, 1u << SH_A, 1u << SH_B, ma, mb, 2u, 1u, lw, ls);
+                apply_pair<SnT, EB>(sn, words, rowa, rowb, 1u << SH_A, 1u << SH_B, ma, mb, 2u, 1u, lw, ls, tails);
             }
           }
           ndraw += 32u;

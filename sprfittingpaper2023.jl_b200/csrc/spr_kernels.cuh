@@ -1,6 +1,7 @@
 // spr_kernels.cuh -- argument blocks and launch wrappers shared by spr_kernels.cu and spr_api.cu
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 namespace spr {
@@ -69,8 +70,13 @@ constexpr int K1_WPC = 7;          // warps per CTA at full occupancy: 4 CTAs x 
 constexpr int K1_MAX_WARPS = 28;   // 72 registers per thread
 
 // packed table entries: 10 bits (3 per word) while every particle index and the EMPTY marker fit, else 16 (2 per word)
-inline int entry_bits(int N) { return N <= 1023 ? 10 : 16; }
-inline int entries_per_word(int N) { return N <= 1023 ? 3 : 2; }
+// (SPRB200_ENTRY_BITS=16 forces the 16-bit rows: experiment hook)
+inline bool force_wide_entries() {
+    static const bool wide = [] { const char *e = std::getenv("SPRB200_ENTRY_BITS"); return e && std::atoi(e) == 16; }();
+    return wide;
+}
+inline int entry_bits(int N) { return (N <= 1023 && !force_wide_entries()) ? 10 : 16; }
+inline int entries_per_word(int N) { return entry_bits(N) == 10 ? 3 : 2; }
 
 struct TrajArgs {                       // K1: spr_traj_kernel
     int N, T;
