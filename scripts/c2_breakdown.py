@@ -16,8 +16,8 @@ for b in range(10):
     eng.build_indices(grid, sim, run, idx)
     st = eng.stats()
     tot_ms += st["device_ms"]; tot_ev += st["events"]
-    print("reach %.2f: %8.1f ms  events %.3e  ev/s %.3e  traj/s %.3e" % (2 + b * 33 / 9, st["device_ms"], st["events"],
-          st["events"] / st["device_ms"] * 1e3, 1e5 / st["device_ms"] * 1e3), flush=True)
+    print("reach %.2f: %8.1f ms (K2 %6.1f K1 %7.1f)  events %.3e  ev/s %.3e  traj/s %.3e" % (2 + b * 33 / 9, st["device_ms"],
+          st["table_ms"], st["traj_ms"], st["events"], st["events"] / st["device_ms"] * 1e3, 1e5 / st["device_ms"] * 1e3), flush=True)
 print("sum of classes %.1f ms, events %.3e" % (tot_ms, tot_ev))
 eng.build_indices(grid, sim, run, np.arange(1, 10001))
 st = eng.stats()

@@ -91,6 +91,7 @@ struct sprb200_ctx {
     double sur_t0 = 0.0, sur_t1 = 0.0;
     long long sur_P = 0;
     int stage_cap_override = 0;   // SPRB200_STAGE_CAP (test hook): staging stride of K2's distance pass
+    int use_tmem = 1;             // SPRB200_TMEM=0 disables the tensor-memory variant of K1 (row offsets in TMEM, 32 warps per SM)
 };
 
 namespace {
@@ -501,7 +502,9 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                 if (ndefer < n) {
                     TrajLayout lay;
                     const bool wide_sn = ctr[CTR_MAX_DEGREE] > 127ULL, wide_off = ctr[CTR_MAX_ENTRIES] > 65535ULL;
-                    if (!make_traj_layout(N, wide_sn, wide_off, h->smem_optin, h->smem_per_sm, &lay)) {
+                    // the tensor-memory variant has a fixed CTA shape: only for launches that fill the GPU
+                    const bool want_tmem = h->use_tmem && h->max_warps == 0 && n >= (long long)32 * h->num_sms;
+                    if (!make_traj_layout(N, wide_sn, wide_off, h->smem_optin, h->smem_per_sm, &lay, want_tmem)) {
                         free_graphs();
                         return fail(h, SPRB200_ERR_TOO_LARGE,
                                     "per-trajectory state (N=" + std::to_string(N) + ", max degree " +
@@ -516,7 +519,7 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                     // a launch that cannot fill the GPU (C1 / C4 / post-fit re-simulation: a few hundred to a few
                     // thousand trajectories) runs narrower CTAs, so that the block scheduler spreads the warps
                     // evenly over all SMs and their four schedulers instead of stacking 7 per CTA
-                    {
+                    if (!lay.tmem) {
                         const long long full = (long long)lay.cta_per_sm * lay.wpc * h->num_sms;
                         if (n < full) {
                             const long long per_sm = (n + h->num_sms - 1) / h->num_sms;      // warps per SM if spread evenly
@@ -837,6 +840,7 @@ int sprb200_create(int device_ordinal, sprb200_handle *out) {
     }
     if (const char *env = std::getenv("SPRB200_MAX_WARPS")) h->max_warps = std::atoi(env);
     if (const char *env = std::getenv("SPRB200_STAGE_CAP")) h->stage_cap_override = std::atoi(env);
+    if (const char *env = std::getenv("SPRB200_TMEM")) h->use_tmem = std::atoi(env);
     if (const char *env = std::getenv("SPRB200_CAP_SCALE")) {
         const double v = std::atof(env);
         if (v > 0.0 && v <= 1.0) h->est_scale = v;

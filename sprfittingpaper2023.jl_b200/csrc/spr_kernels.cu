@@ -395,11 +395,34 @@ __device__ __forceinline__ uint32_t ld_entry(const uint32_t *__restrict__ words,
     return (w >> ls) & PackTraits<EB>::EMPTY;
 }
 
-template <typename OffT, int EB>
-__device__ __forceinline__ NbrRow load_row(const uint32_t *__restrict__ words, const OffT *off, int m, int lw, int ls) {
+// Where the rows start.  TM = false: off[N+1] in the warp's shared-memory slice (2 or 4 B per particle).
+// TM = true: the warp's 32 x 32-word block of TENSOR MEMORY holds (first word | words << 16) of particle p at
+// (lane p & 31, column p >> 5): tcgen05.ld fetches the column of p (one word per lane), a shuffle broadcasts the lane
+// of p -- three instructions like the two LDS + subtract of the shared-memory form, and 2 B per particle of shared
+// memory become free: 6 B per particle, 32 trajectories per SM at 64 registers (N <= 1024, rows < 65,536 words).
+template <bool TM, typename OffT>
+struct RowIndex {
+    const OffT *off;     // TM = false
+    uint32_t taddr;      // TM = true: tensor-memory address of the warp's block (lane quadrant << 16 | first column)
+    __device__ __forceinline__ void bounds(int m, int &o0, int &nw) const {
+        if (TM) {
+            uint32_t v;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr + (uint32_t)(m >> 5)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            v = __shfl_sync(FULL, v, m & 31);
+            o0 = (int)(v & 0xffffu);
+            nw = (int)(v >> 16);
+        } else {
+            o0 = (int)off[m];
+            nw = (int)off[m + 1] - o0;
+        }
+    }
+};
+
+template <bool TM, typename OffT, int EB>
+__device__ __forceinline__ NbrRow load_row(const uint32_t *__restrict__ words, const RowIndex<TM, OffT> &ri, int m, int lw, int ls) {
     NbrRow r;
-    r.o0 = (int)off[m];
-    r.nw = (int)off[m + 1] - r.o0;
+    ri.bounds(m, r.o0, r.nw);
     r.j = ld_entry<EB>(words, r.o0, r.nw, lw, ls);
     return r;
 }
@@ -500,9 +523,10 @@ __device__ __noinline__ int cl_make_room(uint16_t *ab, int cs, int C, int lo, in
 
 // up to K1_WPC warps per CTA, 4 CTAs per SM: 28 trajectories per SM at 72 registers and 8 B of shared memory per
 // particle (N = 1000); small batches run with fewer warps per CTA so that they spread over all SMs
-template <typename SnT, typename OffT, int EB>
-__global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs a) {
+template <typename SnT, typename OffT, int EB, bool TM>
+__global__ void __launch_bounds__(TM ? 32 * K1_WPC_TM : 32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_tmem;
     using ST = SnTraits<SnT>;
     using PT = PackTraits<EB>;
     constexpr int SH_A = ST::SH_A, SH_B = ST::SH_B;
@@ -518,6 +542,23 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
     // convergence check (with threadIdx.x >> 5 used directly the same source compiles to 25 BRA.DIV checks, 64
     // BSSY/BSYNC pairs and 27 % more instructions).
     unsigned char *slice = smem_raw + (size_t)__shfl_sync(FULL, threadIdx.x >> 5, 0) * (size_t)a.lay.slice;
+    RowIndex<TM, OffT> ri;
+    ri.off = reinterpret_cast<const OffT *>(slice + a.lay.o_off);
+    ri.taddr = 0u;
+    if (TM) {
+        // one warp allocates the CTA's tensor-memory columns (32 per group of four warps: a warp reaches only the 32
+        // lanes of its quadrant, warps w and w + 4 share a quadrant and take different column blocks)
+        if ((threadIdx.x >> 5) == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"((uint32_t)__cvta_generic_to_shared(&s_tmem)), "n"(K1_TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint32_t w = (uint32_t)__shfl_sync(FULL, threadIdx.x >> 5, 0);
+        ri.taddr = s_tmem + (((w & 3u) * 32u) << 16) + (w >> 2) * 32u;
+    }
     OffT *off = reinterpret_cast<OffT *>(slice + a.lay.o_off);
     SnT *sn = reinterpret_cast<SnT *>(slice + a.lay.o_sn);
     uint16_t *ab = reinterpret_cast<uint16_t *>(slice + a.lay.o_ab);    // A from the front, B from the back, C in the gap
@@ -545,12 +586,26 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
         const uint32_t *__restrict__ goff = reinterpret_cast<const uint32_t *>((uintptr_t)rec);
         const uint32_t *__restrict__ words =
             reinterpret_cast<const uint32_t *>((uintptr_t)rec + (((size_t)(N + 1) * 4 + 15) & ~(size_t)15));
-        for (int i = lane; i <= N; i += 32) off[i] = (OffT)goff[i];
+        if (TM) {
+#pragma unroll 1
+            for (int c = 0; c < 32; ++c) {
+                const int p = c * 32 + lane;
+                uint32_t v = 0u;
+                if (p < N) {
+                    const uint32_t g0 = goff[p];
+                    v = g0 | ((goff[p + 1] - g0) << 16);
+                }
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(ri.taddr + (uint32_t)c), "r"(v));
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        } else {
+            for (int i = lane; i <= N; i += 32) off[i] = (OffT)goff[i];
+        }
         __syncwarp();
         // ---- initial state: everything A (forward_simulator.jl:148-149); nA = degree = valid entries of the row
         int maxnw = 0;
         for (int i = lane; i < N; i += 32) {
-            const int o0 = (int)off[i], nw = (int)off[i + 1] - o0;
+            const int o0 = (int)goff[i], nw = (int)goff[i + 1] - o0;
             maxnw = max(maxnw, nw);
             uint32_t deg = 0u;
             if (nw > 0) {
@@ -692,7 +747,7 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
                 nAB += dAB * ((int)((v >> SH_A) & CMASK) - (int)((v >> SH_B) & CMASK));
                 sn[m] = (SnT)((v & ~3u) | (isab ? ST_B : ST_A));       // idempotent: every lane stores the same word
                 const uint32_t dlt = (1u << SH_B) - (1u << SH_A);
-                const NbrRow rowm = load_row<OffT, EB>(words, off, m, lw, ls);
+                const NbrRow rowm = load_row<TM, OffT, EB>(words, ri, m, lw, ls);
                 apply_row<false, SnT, EB>(sn, rowm, isab ? dlt : 0u - dlt, 0u, 0u);
                 if (tails && rowm.nw > PT::WPP)
                     apply_row_tail<false, SnT, EB>(sn, words, rowm, isab ? dlt : 0u - dlt, 0u, 0u, lw, ls);
@@ -730,8 +785,7 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
                 // the update below
                 int ysel = 0;
                 NbrRow rowx;
-                rowx.o0 = (int)off[xsel];
-                rowx.nw = (int)off[xsel + 1] - rowx.o0;
+                ri.bounds(xsel, rowx.o0, rowx.nw);
                 rowx.j = EMPTY;
                 for (int w0 = 0; w0 < rowx.nw; w0 += PT::WPP) {
                     const uint32_t j = ld_entry<EB>(words, rowx.o0, rowx.nw, w0 + lw, ls);
@@ -770,7 +824,7 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
                 const uint32_t va = sn[ma], vb = sn[mb];
                 // a's neighbours lose an A neighbour, and b (one of them) drops B(2) -> C(0);
                 // b's neighbours lose a B neighbour, and a drops A(1) -> C(0)
-                const NbrRow rowy = load_row<OffT, EB>(words, off, ysel, lw, ls);
+                const NbrRow rowy = load_row<TM, OffT, EB>(words, ri, ysel, lw, ls);
                 NbrRow rowa, rowb;                  // selected by value: both stay in registers
                 rowa.o0 = sideA ? rowx.o0 : rowy.o0; rowa.nw = sideA ? rowx.nw : rowy.nw; rowa.j = sideA ? rowx.j : rowy.j;
                 rowb.o0 = sideA ? rowy.o0 : rowx.o0; rowb.nw = sideA ? rowy.nw : rowx.nw; rowb.j = sideA ? rowy.j : rowx.j;
@@ -799,8 +853,8 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
                 const uint32_t va = sn[ma], vb = sn[mb];
                 // a's neighbours gain an A neighbour, and b becomes B: C(0) -> B(2);
                 // b's neighbours gain a B neighbour, and a becomes A: C(0) -> A(1)
-                const NbrRow rowa = load_row<OffT, EB>(words, off, ma, lw, ls);
-                const NbrRow rowb = load_row<OffT, EB>(words, off, mb, lw, ls);
+                const NbrRow rowa = load_row<TM, OffT, EB>(words, ri, ma, lw, ls);
+                const NbrRow rowb = load_row<TM, OffT, EB>(words, ri, mb, lw, ls);
                 nAB += (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) + 1;
                 __syncwarp();
                 apply_pair<SnT, EB>(sn, words, rowa, rowb, 1u << SH_A, 1u << SH_B, ma, mb, 2u, 1u, lw, ls, tails);
@@ -819,6 +873,12 @@ __global__ void __launch_bounds__(32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs
         }
         if (lane == 0) atomicAdd(a.nevents + slot, (unsigned long long)(ndraw - nskip));
         __syncwarp();
+    }
+    if (TM) {
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();                 // every warp of the CTA is done with its block
+        if ((threadIdx.x >> 5) == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(s_tmem), "n"(K1_TMEM_COLS));
     }
 }
 
@@ -1118,11 +1178,11 @@ cudaError_t set_table_attr(int bytes) {
     return cudaSuccess;
 }
 
-template <typename SnT, typename OffT, int EB>
+template <typename SnT, typename OffT, int EB, bool TM>
 cudaError_t set_traj_attr(int bytes) {
     static int configured = -1;
     if (bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<SnT, OffT, EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<SnT, OffT, EB, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
         configured = bytes;
     }
@@ -1169,13 +1229,14 @@ cudaError_t launch_table(const TableArgs &a, int DIM, int nblocks, cudaStream_t 
     return cudaGetLastError();
 }
 
-bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int smem_per_sm, TrajLayout *out) {
+bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int smem_per_sm, TrajLayout *out, bool tmem) {
     TrajLayout l{};
     l.wide_sn = wide_sn ? 1 : 0;
     l.wide_off = wide_off ? 1 : 0;
     l.eb = entry_bits(N);
+    l.tmem = (tmem && !wide_sn && !wide_off && l.eb == 10 && N <= 1024) ? 1 : 0;
     int o = 0;
-    l.o_off = o;  o += align16((N + 1) * (wide_off ? 4 : 2));
+    l.o_off = o;  if (!l.tmem) o += align16((N + 1) * (wide_off ? 4 : 2));
     l.o_sn = o;   o += align16(N * (wide_sn ? 4 : 2));
     l.o_ab = o;   o += align16(N * 2);
     l.o_pos = o;  o += align16(N * 2);
@@ -1183,6 +1244,13 @@ bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int sm
     // warps per CTA: most resident trajectories per SM (every CTA also costs 1 KB of reserved shared memory);
     // 72 registers allow 28 warps per SM
     int best = 0, best_w = 0, best_c = 0;
+    if (l.tmem) {
+        // fixed shape: 8 warps per CTA (two column blocks of 32 per lane quadrant), 4 CTAs per SM, 64 registers
+        l.wpc = K1_WPC_TM;
+        l.cta_per_sm = 4;
+        *out = l;
+        return (long long)l.wpc * l.slice <= smem_optin && 4LL * ((long long)l.wpc * l.slice + 1024) <= smem_per_sm;
+    }
     for (int w = 1; w <= K1_WPC; ++w) {
         const long long bytes = (long long)w * l.slice;
         if (bytes > smem_optin) break;
@@ -1203,14 +1271,20 @@ cudaError_t launch_traj(const TrajArgs &a, int nblocks, cudaStream_t st) {
         using S_ = decltype(sn_t);
         using O_ = decltype(off_t);
         const int bytes = a.lay.slice * a.lay.wpc;
-        if (a.lay.eb == 10) {
-            cudaError_t e = set_traj_attr<S_, O_, 10>(bytes);
+        if (a.lay.tmem) {
+            // row offsets in tensor memory: 16-bit states and offsets, 10-bit entries only (N <= 1023)
+            if (!std::is_same<S_, uint16_t>::value || !std::is_same<O_, uint16_t>::value || a.lay.eb != 10) return cudaErrorInvalidValue;
+            cudaError_t e = set_traj_attr<uint16_t, uint16_t, 10, true>(bytes);
             if (e != cudaSuccess) return e;
-            spr_traj_kernel<S_, O_, 10><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+            spr_traj_kernel<uint16_t, uint16_t, 10, true><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+        } else if (a.lay.eb == 10) {
+            cudaError_t e = set_traj_attr<S_, O_, 10, false>(bytes);
+            if (e != cudaSuccess) return e;
+            spr_traj_kernel<S_, O_, 10, false><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
         } else {
-            cudaError_t e = set_traj_attr<S_, O_, 16>(bytes);
+            cudaError_t e = set_traj_attr<S_, O_, 16, false>(bytes);
             if (e != cudaSuccess) return e;
-            spr_traj_kernel<S_, O_, 16><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+            spr_traj_kernel<S_, O_, 16, false><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
         }
         return cudaGetLastError();
     });

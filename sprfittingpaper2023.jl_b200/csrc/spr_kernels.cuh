@@ -62,12 +62,15 @@ struct TrajLayout {
     int wide_sn;    // SnT = uint32_t (15-bit neighbour counts) instead of uint16_t (7-bit)
     int wide_off;   // OffT = uint32_t (more than 65535 words of packed rows)
     int eb;         // bits per packed table entry (10 or 16)
+    int tmem;       // row offsets in tensor memory instead of o_off (6 B of shared memory per particle, 32 warps per SM)
     int wpc;        // warps (trajectories) per CTA
     int cta_per_sm;
 };
 
 constexpr int K1_WPC = 7;          // warps per CTA at full occupancy: 4 CTAs x 7 warps = 28 trajectories per SM
 constexpr int K1_MAX_WARPS = 28;   // 72 registers per thread
+constexpr int K1_WPC_TM = 8;       // tensor-memory variant: 4 CTAs x 8 warps = 32 trajectories per SM, 64 registers
+constexpr int K1_TMEM_COLS = 64;   // tensor-memory columns per CTA (two blocks of 32 per lane quadrant)
 
 // packed table entries: 10 bits (3 per word) while every particle index and the EMPTY marker fit, else 16 (2 per word)
 // (SPRB200_ENTRY_BITS=16 forces the 16-bit rows: experiment hook)
@@ -129,7 +132,7 @@ cudaError_t launch_table(const TableArgs &a, int DIM, int nblocks, cudaStream_t 
 constexpr int K2_THREADS = 256;
 
 // K1: picks the warps-per-CTA that keeps the most trajectories resident per SM; false if one slice does not fit
-bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int smem_per_sm, TrajLayout *out);
+bool make_traj_layout(int N, bool wide_sn, bool wide_off, int smem_optin, int smem_per_sm, TrajLayout *out, bool tmem = false);
 cudaError_t launch_traj(const TrajArgs &a, int nblocks, cudaStream_t st);
 
 // fixed-position neighbour table (K2b): FP64, the reference's periodic_dist_sq.
