@@ -131,3 +131,34 @@ def test_fixed_positions_bit_exact(engine, oracle_libs):
         for r in range(4):
             b, c, ev = M.trajectory(m, *p, 5, 2 + k, r, observable=2)
             assert np.array_equal(B[k, r], b) and np.array_equal(C[k, r], c)
+
+
+def test_tensor_memory_variant_bit_exact(engine, oracle_libs, monkeypatch):
+    """K1 with the row offsets in tensor memory (tcgen05.ld/st; used when a launch fills the GPU: >= 32 trajectories
+    per SM) against the same launch with the offsets in shared memory (SPRB200_TMEM=0, read at sprb200_create) and
+    against the sequential mirror: raw curves, moments and event counts, dense and sparse tables, flips and pairs."""
+    import sprb200
+    from sprb200 import _lib
+    from oracle import mirror_oracle as M
+    g, m = _sims(tstop=60.0, toff=25.0, tsave=np.arange(0.0, 61.0, 1.0))
+    pts = np.array([[0.5, 0.3, 3.0, 35.0], [0.05, 0.02, 0.5, 15.3], [2.0, 1.0, 0.0, 24.0], [1.0, 0.1, 1.0, 30.0]])
+    nrep = 1600                                   # 6,400 trajectories > 32 x 148: the tensor-memory launch shape
+    run = sprb200.make_run(nsims=nrep, seed=99, param_index_base=40)
+    a = engine.simulate(g, pts, run)
+    assert engine.stats()["trajectories"] == 4 * nrep
+    monkeypatch.setenv("SPRB200_TMEM", "0")
+    plain = sprb200.Engine(0)
+    try:
+        b = plain.simulate(g, pts, run)
+    finally:
+        plain.close()
+    for k in ("sum", "sumsq", "n_used", "n_events"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["sum"][:, 1:].min() > 0
+    # raw curves of a few replicates inside the same big launch against the mirror
+    B, C, nev = engine.simulate_raw(g, pts, sprb200.make_run(nsims=nrep, seed=99, param_index_base=40))
+    for k in (0, 3):
+        for r in (0, 7, nrep - 1):
+            bb, cc, _ = M.trajectory(m, *pts[k], 99, 40 + k, r, observable=2)
+            assert np.array_equal(B[k, r], bb) and np.array_equal(C[k, r], cc), (k, r)
+    assert np.array_equal(B.astype(np.int64).sum(axis=1) + C.astype(np.int64).sum(axis=1), a["sum"])
