@@ -91,6 +91,7 @@ struct sprb200_ctx {
     double sur_t0 = 0.0, sur_t1 = 0.0;
     long long sur_P = 0;
     int stage_cap_override = 0;   // SPRB200_STAGE_CAP (test hook): staging stride of K2's distance pass
+    int use_smem_table = 1;       // SPRB200_SMEM_TABLE=0 disables the rows-in-shared-memory variant of underfilled launches
     int use_tmem = 1;             // SPRB200_TMEM=0 disables the tensor-memory variant of K1 (row offsets in TMEM, 32 warps per SM)
 };
 
@@ -519,7 +520,25 @@ int run_points(sprb200_ctx *h, const RunPlan &plan, const PointDev *pts, const u
                     // a launch that cannot fill the GPU (C1 / C4 / post-fit re-simulation: a few hundred to a few
                     // thousand trajectories) runs narrower CTAs, so that the block scheduler spreads the warps
                     // evenly over all SMs and their four schedulers instead of stacking 7 per CTA
-                    if (!lay.tmem) {
+                    // ... and, when every trajectory of the launch can be resident WITH its neighbour rows in shared
+                    // memory, one-warp CTAs that copy the rows in once: each row load is then an LDS instead of an L2
+                    // round trip, which is what a half-empty GPU is waiting for (per-event latency, not issue slots)
+                    if (!lay.tmem && !wide_sn && !wide_off && lay.eb == 10 && h->use_smem_table && h->max_warps == 0 &&
+                        ctr[CTR_MAX_ENTRIES] > 0) {
+                        const size_t tbl = align16z(sizeof(uint32_t) * (size_t)ctr[CTR_MAX_ENTRIES]);
+                        const size_t per = (size_t)lay.slice + tbl;
+                        if (per <= (size_t)h->smem_optin) {
+                            const long long c = std::min<long long>(K1_MAX_WARPS, (long long)(h->smem_per_sm / (per + 1024)));
+                            if (c >= 1 && n <= c * h->num_sms) {
+                                lay.o_tbl = lay.slice;
+                                lay.tbl_words = (int)ctr[CTR_MAX_ENTRIES];
+                                lay.slice = (int)per;
+                                lay.wpc = 1;
+                                lay.cta_per_sm = (int)c;
+                            }
+                        }
+                    }
+                    if (!lay.tmem && lay.tbl_words == 0) {
                         const long long full = (long long)lay.cta_per_sm * lay.wpc * h->num_sms;
                         if (n < full) {
                             const long long per_sm = (n + h->num_sms - 1) / h->num_sms;      // warps per SM if spread evenly
@@ -841,6 +860,7 @@ int sprb200_create(int device_ordinal, sprb200_handle *out) {
     if (const char *env = std::getenv("SPRB200_MAX_WARPS")) h->max_warps = std::atoi(env);
     if (const char *env = std::getenv("SPRB200_STAGE_CAP")) h->stage_cap_override = std::atoi(env);
     if (const char *env = std::getenv("SPRB200_TMEM")) h->use_tmem = std::atoi(env);
+    if (const char *env = std::getenv("SPRB200_SMEM_TABLE")) h->use_smem_table = std::atoi(env);
     if (const char *env = std::getenv("SPRB200_CAP_SCALE")) {
         const double v = std::atof(env);
         if (v > 0.0 && v <= 1.0) h->est_scale = v;

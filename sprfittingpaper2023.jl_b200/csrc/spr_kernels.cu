@@ -372,10 +372,13 @@ template <> struct SnTraits<uint32_t> { static constexpr int SH_A = 2, SH_B = 17
 
 // EB = 10: three entries per word, lanes 0..29 take the entries of 10 words per pass; EB = 16: two per word, 32
 // lanes take 16 words per pass.  A lane's word (lw) and shift (ls) inside a pass are constants of the lane.
-template <int EB> struct PackTraits {
-    static constexpr int EPW = EB == 10 ? 3 : 2;
+// TS: the packed rows of the trajectory were copied into the warp's shared-memory slice (launches that cannot fill
+// the GPU: every row load is then an LDS instead of an L2 round trip); else they are read from the record in global memory.
+template <int EB_, bool TS_> struct PackTraits {
+    static constexpr int EPW = EB_ == 10 ? 3 : 2;
     static constexpr int WPP = 32 / EPW;               // words per pass
-    static constexpr uint32_t EMPTY = (1u << EB) - 1u;
+    static constexpr uint32_t EMPTY = (1u << EB_) - 1u;
+    static __device__ __forceinline__ uint32_t ld(const uint32_t *w, uint32_t i) { return TS_ ? w[i] : __ldg(w + i); }
 };
 
 // Neighbour updates are split into a load (row offset, length, this lane's neighbour) and an apply
@@ -388,11 +391,11 @@ struct NbrRow {
 };
 
 // table words are written by K2 (an earlier launch) and only read here
-template <int EB>
-__device__ __forceinline__ uint32_t ld_entry(const uint32_t *__restrict__ words, int o0, int nw, int wi, int ls) {
+template <typename P>
+__device__ __forceinline__ uint32_t ld_entry(const uint32_t *words, int o0, int nw, int wi, int ls) {
     uint32_t w = 0xffffffffu;                          // every entry EMPTY
-    if (wi < nw) w = __ldg(words + (uint32_t)(o0 + wi));
-    return (w >> ls) & PackTraits<EB>::EMPTY;
+    if (wi < nw) w = P::ld(words, (uint32_t)(o0 + wi));
+    return (w >> ls) & P::EMPTY;
 }
 
 // Where the rows start.  TM = false: off[N+1] in the warp's shared-memory slice (2 or 4 B per particle).
@@ -419,33 +422,33 @@ struct RowIndex {
     }
 };
 
-template <bool TM, typename OffT, int EB>
-__device__ __forceinline__ NbrRow load_row(const uint32_t *__restrict__ words, const RowIndex<TM, OffT> &ri, int m, int lw, int ls) {
+template <bool TM, typename OffT, typename P>
+__device__ __forceinline__ NbrRow load_row(const uint32_t *words, const RowIndex<TM, OffT> &ri, int m, int lw, int ls) {
     NbrRow r;
     ri.bounds(m, r.o0, r.nw);
-    r.j = ld_entry<EB>(words, r.o0, r.nw, lw, ls);
+    r.j = ld_entry<P>(words, r.o0, r.nw, lw, ls);
     return r;
 }
 
 // sn[j] += delta for every neighbour j of the row; the neighbour `other` (the partner of a pair event)
 // also takes `extra`, its own state change.  apply_row covers the first pass (one neighbour per lane),
 // apply_row_tail the rest (more than WPP words: rare).
-template <bool PAIR, typename SnT, int EB>
+template <bool PAIR, typename SnT, typename P>
 __device__ __forceinline__ void apply_row(SnT *sn, const NbrRow &r, uint32_t delta, uint32_t other, uint32_t extra) {
-    if (r.j != PackTraits<EB>::EMPTY) {
+    if (r.j != P::EMPTY) {
         uint32_t d = delta;
         if (PAIR && r.j == other) d += extra;
         sn[r.j] = (SnT)((uint32_t)sn[r.j] + d);
     }
 }
 
-template <bool PAIR, typename SnT, int EB>
-__device__ __forceinline__ void apply_row_tail(SnT *sn, const uint32_t *__restrict__ words, const NbrRow &r, uint32_t delta,
+template <bool PAIR, typename SnT, typename P>
+__device__ __forceinline__ void apply_row_tail(SnT *sn, const uint32_t *words, const NbrRow &r, uint32_t delta,
                                                uint32_t other, uint32_t extra, int lw, int ls) {
 #pragma unroll 1
-    for (int wi = lw + PackTraits<EB>::WPP; wi < r.nw; wi += PackTraits<EB>::WPP) {
-        const uint32_t j = ld_entry<EB>(words, r.o0, r.nw, wi, ls);
-        if (j != PackTraits<EB>::EMPTY) {
+    for (int wi = lw + P::WPP; wi < r.nw; wi += P::WPP) {
+        const uint32_t j = ld_entry<P>(words, r.o0, r.nw, wi, ls);
+        if (j != P::EMPTY) {
             uint32_t d = delta;
             if (PAIR && j == other) d += extra;
             sn[j] = (SnT)((uint32_t)sn[j] + d);
@@ -455,18 +458,18 @@ __device__ __forceinline__ void apply_row_tail(SnT *sn, const uint32_t *__restri
 
 // both rows of a pair event: every phase touches each state word at most once and the phases are separated
 // by __syncwarp(), so the order of the additions is immaterial; ONE uniform branch covers both tails
-template <typename SnT, int EB>
-__device__ __forceinline__ void apply_pair(SnT *sn, const uint32_t *__restrict__ words, const NbrRow &ra, const NbrRow &rb,
+template <typename SnT, typename P>
+__device__ __forceinline__ void apply_pair(SnT *sn, const uint32_t *words, const NbrRow &ra, const NbrRow &rb,
                                            uint32_t da, uint32_t db, int ma, int mb, uint32_t ea, uint32_t eb, int lw, int ls,
                                            bool tails) {
-    apply_row<true, SnT, EB>(sn, ra, da, (uint32_t)mb, ea);
+    apply_row<true, SnT, P>(sn, ra, da, (uint32_t)mb, ea);
     __syncwarp();
-    apply_row<true, SnT, EB>(sn, rb, db, (uint32_t)ma, eb);
+    apply_row<true, SnT, P>(sn, rb, db, (uint32_t)ma, eb);
     __syncwarp();
-    if (tails && max(ra.nw, rb.nw) > PackTraits<EB>::WPP) {
-        apply_row_tail<true, SnT, EB>(sn, words, ra, da, (uint32_t)mb, ea, lw, ls);
+    if (tails && max(ra.nw, rb.nw) > P::WPP) {
+        apply_row_tail<true, SnT, P>(sn, words, ra, da, (uint32_t)mb, ea, lw, ls);
         __syncwarp();
-        apply_row_tail<true, SnT, EB>(sn, words, rb, db, (uint32_t)ma, eb, lw, ls);
+        apply_row_tail<true, SnT, P>(sn, words, rb, db, (uint32_t)ma, eb, lw, ls);
         __syncwarp();
     }
 }
@@ -523,12 +526,12 @@ __device__ __noinline__ int cl_make_room(uint16_t *ab, int cs, int C, int lo, in
 
 // up to K1_WPC warps per CTA, 4 CTAs per SM: 28 trajectories per SM at 72 registers and 8 B of shared memory per
 // particle (N = 1000); small batches run with fewer warps per CTA so that they spread over all SMs
-template <typename SnT, typename OffT, int EB, bool TM>
+template <typename SnT, typename OffT, int EB, bool TM, bool TS>
 __global__ void __launch_bounds__(TM ? 32 * K1_WPC_TM : 32 * K1_WPC, 4) spr_traj_kernel(const TrajArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_tmem;
     using ST = SnTraits<SnT>;
-    using PT = PackTraits<EB>;
+    using PT = PackTraits<EB, TS>;
     constexpr int SH_A = ST::SH_A, SH_B = ST::SH_B;
     constexpr uint32_t CMASK = ST::MASK;
     constexpr uint32_t EMPTY = PT::EMPTY;
@@ -584,8 +587,17 @@ __global__ void __launch_bounds__(TM ? 32 * K1_WPC_TM : 32 * K1_WPC, 4) spr_traj
 
         // ---- neighbour table: row offsets into shared memory, packed rows stay in global memory
         const uint32_t *__restrict__ goff = reinterpret_cast<const uint32_t *>((uintptr_t)rec);
-        const uint32_t *__restrict__ words =
+        const uint32_t *gwords =
             reinterpret_cast<const uint32_t *>((uintptr_t)rec + (((size_t)(N + 1) * 4 + 15) & ~(size_t)15));
+        const uint32_t *words = gwords;
+        if (TS) {
+            // the launch cannot fill the GPU: the rows go into the warp's slice once (coalesced), every row load of
+            // the trajectory is then a shared-memory load
+            uint32_t *tw = reinterpret_cast<uint32_t *>(slice + a.lay.o_tbl);
+            const int nwt = (int)goff[N];
+            for (int i = lane; i < nwt; i += 32) tw[i] = __ldg(gwords + i);
+            words = tw;
+        }
         if (TM) {
 #pragma unroll 1
             for (int c = 0; c < 32; ++c) {
@@ -610,7 +622,7 @@ __global__ void __launch_bounds__(TM ? 32 * K1_WPC_TM : 32 * K1_WPC, 4) spr_traj
             uint32_t deg = 0u;
             if (nw > 0) {
                 // every word but the last is full; the last one holds 1..EPW entries
-                const uint32_t wl = __ldg(words + (uint32_t)(o0 + nw - 1));
+                const uint32_t wl = __ldg(gwords + (uint32_t)(o0 + nw - 1));
                 deg = (uint32_t)(nw - 1) * PT::EPW;
 #pragma unroll
                 for (int e = 0; e < PT::EPW; ++e) deg += ((wl >> (e * EB)) & EMPTY) != EMPTY ? 1u : 0u;
@@ -747,10 +759,10 @@ __global__ void __launch_bounds__(TM ? 32 * K1_WPC_TM : 32 * K1_WPC, 4) spr_traj
                 nAB += dAB * ((int)((v >> SH_A) & CMASK) - (int)((v >> SH_B) & CMASK));
                 sn[m] = (SnT)((v & ~3u) | (isab ? ST_B : ST_A));       // idempotent: every lane stores the same word
                 const uint32_t dlt = (1u << SH_B) - (1u << SH_A);
-                const NbrRow rowm = load_row<TM, OffT, EB>(words, ri, m, lw, ls);
-                apply_row<false, SnT, EB>(sn, rowm, isab ? dlt : 0u - dlt, 0u, 0u);
+                const NbrRow rowm = load_row<TM, OffT, PT>(words, ri, m, lw, ls);
+                apply_row<false, SnT, PT>(sn, rowm, isab ? dlt : 0u - dlt, 0u, 0u);
                 if (tails && rowm.nw > PT::WPP)
-                    apply_row_tail<false, SnT, EB>(sn, words, rowm, isab ? dlt : 0u - dlt, 0u, 0u, lw, ls);
+                    apply_row_tail<false, SnT, PT>(sn, words, rowm, isab ? dlt : 0u - dlt, 0u, 0u, lw, ls);
                 __syncwarp();
             } else if (x < cP) {
                 // A + B --> C (:256-289): pair number k of the nAB active pairs, enumerated along the
@@ -788,7 +800,7 @@ __global__ void __launch_bounds__(TM ? 32 * K1_WPC_TM : 32 * K1_WPC, 4) spr_traj
                 ri.bounds(xsel, rowx.o0, rowx.nw);
                 rowx.j = EMPTY;
                 for (int w0 = 0; w0 < rowx.nw; w0 += PT::WPP) {
-                    const uint32_t j = ld_entry<EB>(words, rowx.o0, rowx.nw, w0 + lw, ls);
+                    const uint32_t j = ld_entry<PT>(words, rowx.o0, rowx.nw, w0 + lw, ls);
                     if (w0 == 0) rowx.j = j;
                     const bool ok = j != EMPTY && ((uint32_t)sn[j != EMPTY ? j : 0u] & 3u) == want;
                     const uint32_t bal = __ballot_sync(FULL, ok);
@@ -824,13 +836,13 @@ __global__ void __launch_bounds__(TM ? 32 * K1_WPC_TM : 32 * K1_WPC, 4) spr_traj
                 const uint32_t va = sn[ma], vb = sn[mb];
                 // a's neighbours lose an A neighbour, and b (one of them) drops B(2) -> C(0);
                 // b's neighbours lose a B neighbour, and a drops A(1) -> C(0)
-                const NbrRow rowy = load_row<TM, OffT, EB>(words, ri, ysel, lw, ls);
+                const NbrRow rowy = load_row<TM, OffT, PT>(words, ri, ysel, lw, ls);
                 NbrRow rowa, rowb;                  // selected by value: both stay in registers
                 rowa.o0 = sideA ? rowx.o0 : rowy.o0; rowa.nw = sideA ? rowx.nw : rowy.nw; rowa.j = sideA ? rowx.j : rowy.j;
                 rowb.o0 = sideA ? rowy.o0 : rowx.o0; rowb.nw = sideA ? rowy.nw : rowx.nw; rowb.j = sideA ? rowy.j : rowx.j;
                 nAB -= (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) - 1;
                 __syncwarp();   // every lane has read va, vb before the partner words change
-                apply_pair<SnT, EB>(sn, words, rowa, rowb, 0u - (1u << SH_A), 0u - (1u << SH_B), ma, mb, 0u - 2u, 0u - 1u, lw, ls, tails);
+                apply_pair<SnT, PT>(sn, words, rowa, rowb, 0u - (1u << SH_A), 0u - (1u << SH_B), ma, mb, 0u - 2u, 0u - 1u, lw, ls, tails);
             } else {
                 // C --> A + B (:291-344): complex k; the freed end is chosen by a fair coin (:300-307)
                 const int k = (int)__umulhi(vw, (uint32_t)cntC);
@@ -853,11 +865,11 @@ __global__ void __launch_bounds__(TM ? 32 * K1_WPC_TM : 32 * K1_WPC, 4) spr_traj
                 const uint32_t va = sn[ma], vb = sn[mb];
                 // a's neighbours gain an A neighbour, and b becomes B: C(0) -> B(2);
                 // b's neighbours gain a B neighbour, and a becomes A: C(0) -> A(1)
-                const NbrRow rowa = load_row<TM, OffT, EB>(words, ri, ma, lw, ls);
-                const NbrRow rowb = load_row<TM, OffT, EB>(words, ri, mb, lw, ls);
+                const NbrRow rowa = load_row<TM, OffT, PT>(words, ri, ma, lw, ls);
+                const NbrRow rowb = load_row<TM, OffT, PT>(words, ri, mb, lw, ls);
                 nAB += (int)((va >> SH_B) & CMASK) + (int)((vb >> SH_A) & CMASK) + 1;
                 __syncwarp();
-                apply_pair<SnT, EB>(sn, words, rowa, rowb, 1u << SH_A, 1u << SH_B, ma, mb, 2u, 1u, lw, ls, tails);
+                apply_pair<SnT, PT>(sn, words, rowa, rowb, 1u << SH_A, 1u << SH_B, ma, mb, 2u, 1u, lw, ls, tails);
             }
           }
           ndraw += 32u;
@@ -1178,11 +1190,11 @@ cudaError_t set_table_attr(int bytes) {
     return cudaSuccess;
 }
 
-template <typename SnT, typename OffT, int EB, bool TM>
+template <typename SnT, typename OffT, int EB, bool TM, bool TS>
 cudaError_t set_traj_attr(int bytes) {
     static int configured = -1;
     if (bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<SnT, OffT, EB, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaError_t e = cudaFuncSetAttribute(spr_traj_kernel<SnT, OffT, EB, TM, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
         configured = bytes;
     }
@@ -1274,17 +1286,23 @@ cudaError_t launch_traj(const TrajArgs &a, int nblocks, cudaStream_t st) {
         if (a.lay.tmem) {
             // row offsets in tensor memory: 16-bit states and offsets, 10-bit entries only (N <= 1023)
             if (!std::is_same<S_, uint16_t>::value || !std::is_same<O_, uint16_t>::value || a.lay.eb != 10) return cudaErrorInvalidValue;
-            cudaError_t e = set_traj_attr<uint16_t, uint16_t, 10, true>(bytes);
+            cudaError_t e = set_traj_attr<uint16_t, uint16_t, 10, true, false>(bytes);
             if (e != cudaSuccess) return e;
-            spr_traj_kernel<uint16_t, uint16_t, 10, true><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+            spr_traj_kernel<uint16_t, uint16_t, 10, true, false><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+        } else if (a.lay.tbl_words > 0) {
+            // rows in shared memory (underfilled launches): the common instantiation only
+            if (!std::is_same<S_, uint16_t>::value || !std::is_same<O_, uint16_t>::value || a.lay.eb != 10) return cudaErrorInvalidValue;
+            cudaError_t e = set_traj_attr<uint16_t, uint16_t, 10, false, true>(bytes);
+            if (e != cudaSuccess) return e;
+            spr_traj_kernel<uint16_t, uint16_t, 10, false, true><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
         } else if (a.lay.eb == 10) {
-            cudaError_t e = set_traj_attr<S_, O_, 10, false>(bytes);
+            cudaError_t e = set_traj_attr<S_, O_, 10, false, false>(bytes);
             if (e != cudaSuccess) return e;
-            spr_traj_kernel<S_, O_, 10, false><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+            spr_traj_kernel<S_, O_, 10, false, false><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
         } else {
-            cudaError_t e = set_traj_attr<S_, O_, 16, false>(bytes);
+            cudaError_t e = set_traj_attr<S_, O_, 16, false, false>(bytes);
             if (e != cudaSuccess) return e;
-            spr_traj_kernel<S_, O_, 16, false><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
+            spr_traj_kernel<S_, O_, 16, false, false><<<nblocks, 32 * a.lay.wpc, bytes, st>>>(a);
         }
         return cudaGetLastError();
     });

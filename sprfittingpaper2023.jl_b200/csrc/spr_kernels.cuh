@@ -63,6 +63,8 @@ struct TrajLayout {
     int wide_off;   // OffT = uint32_t (more than 65535 words of packed rows)
     int eb;         // bits per packed table entry (10 or 16)
     int tmem;       // row offsets in tensor memory instead of o_off (6 B of shared memory per particle, 32 warps per SM)
+    int o_tbl;      // u32[tbl_words]  the packed rows themselves, when tbl_words > 0 (underfilled launches, one warp per CTA)
+    int tbl_words;
     int wpc;        // warps (trajectories) per CTA
     int cta_per_sm;
 };
