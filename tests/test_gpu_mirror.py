@@ -154,7 +154,7 @@ def test_tensor_memory_variant_bit_exact(engine, oracle_libs, monkeypatch):
         plain.close()
     for k in ("sum", "sumsq", "n_used", "n_events"):
         assert np.array_equal(a[k], b[k]), k
-    assert a["sum"][:, 1:].min() > 0
+    assert a["sum"][:, 1:20].min() > 0
     # raw curves of a few replicates inside the same big launch against the mirror
     B, C, nev = engine.simulate_raw(g, pts, sprb200.make_run(nsims=nrep, seed=99, param_index_base=40))
     for k in (0, 3):
