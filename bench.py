@@ -178,10 +178,6 @@ def sample_text(r, what):
                os.cpu_count() or 1, r["busy"]))
 
 
-def mean_degree(reach, L):
-    return (NPART - 1) * min(1.0, 4.0 / 3.0 * np.pi * reach ** 3 / L ** 3)
-
-
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"

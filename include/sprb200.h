@@ -141,7 +141,9 @@ int sprb200_last_kernel_ms(sprb200_handle h, double *table_ms, double *traj_ms);
  * out[0] = bytes of shared memory per trajectory, out[1] = trajectories (warps) per CTA, out[2] = CTAs per
  * SM, out[3] = bytes of shared memory of one table-build CTA.  wide_state / wide_offsets select the
  * 32-bit state words (a degree above 127) / offsets (more than 65,535 table entries).
- * SPRB200_ERR_TOO_LARGE when one trajectory does not fit. */
+ * SPRB200_ERR_TOO_LARGE when one trajectory does not fit.  (This is the shared-memory plan; launches that fill the
+ * GPU with N <= 1023 keep the row offsets in tensor memory instead: 6 B of shared memory per particle, 8 warps per CTA,
+ * 4 CTAs per SM.  SPRB200_TMEM=0 in the environment switches that variant off.) */
 int sprb200_traj_layout(int32_t N, int32_t wide_state, int32_t wide_offsets, int32_t out[4]);
 
 /* Rough relative cost (SSA events x neighbour work of one replicate) of each point: the ordering the library

@@ -412,7 +412,7 @@ struct RowIndex {
             uint32_t v;
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr + (uint32_t)(m >> 5)));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            v = __shfl_sync(FULL, v, m & 31);
+            v = __shfl_sync(FULL, v, m);          // the source lane is taken modulo 32
             o0 = (int)(v & 0xffffu);
             nw = (int)(v >> 16);
         } else {
