@@ -329,7 +329,8 @@ def test_gpu_grid_sample_variance_terminator(engine, oracle_libs, gname):
     """the reference's default VarianceTerminator(0.01, 15, 250) on the same grid samples: the number of
     replicates each point uses (callbacks.jl:204-217) is a random stopping time, compared in distribution:
     points that always run to maxsims or always stop at minsims must agree exactly with the oracle, the total
-    over the sample within 8 %, the rank correlation over the points above 0.9; mean curves within 5 SE."""
+    over the sample within 8 %, the points in between within a factor 3 each (median factor < 1.6); mean curves
+    within 5 SE."""
     import sprb200
     from sprb200 import _lib
     from oracle import ref_oracle as R
@@ -357,10 +358,13 @@ def test_gpu_grid_sample_variance_terminator(engine, oracle_libs, gname):
     sure_min = (nu == 15) & (rn == 15)
     assert np.sum((nu == 250) != (rn == 250)) <= 3 and np.sum((nu == 15) != (rn == 15)) <= 3
     assert nu.sum() == pytest.approx(rn.sum(), rel=0.08)
+    # in between, the stopping index is a first-passage time with a broad distribution (the variance estimate of 20-100
+    # replicates is itself 15-30 % noisy): two independent samples agree within a factor, not in rank
     mid = ~(sure_max | sure_min)
-    if mid.sum() >= 5:
-        from scipy.stats import spearmanr
-        assert spearmanr(nu[mid], rn[mid]).statistic > 0.8
+    if mid.any():
+        ratio = nu[mid].astype(float) / rn[mid].astype(float)
+        assert np.all((ratio > 1.0 / 3.0) & (ratio < 3.0)), (nu[mid].tolist(), rn[mid].tolist())
+        assert abs(np.median(np.log(ratio))) < np.log(1.6), (nu[mid].tolist(), rn[mid].tolist())
     # the means of those adaptive samples agree as well (SE from the oracle's own variance estimate)
     # (a Gaussian bound needs enough replicates for the variance estimate and enough counts per bin: points that
     # stop near minsims = 15 are Student-t with ~14 degrees of freedom, bound 9 instead of 5)
