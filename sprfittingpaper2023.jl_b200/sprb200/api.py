@@ -22,17 +22,17 @@ Same names, argument meaning and error behaviour as the Julia package (paths und
   update_pars_and_run_spr_sim, fitted_curves   src/fitting.jl:36-241, 264-278
 
 Everything that simulates runs on the GPU through libsprb200.so; there is no CPU path here.
-The reference writes JLD (HDF5) files; neither Julia nor HDF5 exist in this image, so the Python
-side stores the same keys in an .npz container (see INTEGRATION.md for the Julia shim that writes
-real .jld files with the reference's own writer).
+Files: a file name ending in `.jld` is written and read in the reference's own JLD (HDF5) layout by
+`sprb200/jld.py` (a dependency-free implementation of the part of the HDF5 file format JLD.jl uses; this
+image has neither Julia nor libhdf5 — see that module for what has and has not been verified); any other
+name is an .npz stand-in with the same keys, which the reference cannot load.
 """
 import math
 import os
-import shutil
-
 import numpy as np
 
 from . import _lib
+from . import jld as _jld
 
 DEFAULT_SIM_ANTIGENCONCEN = 500 / 149 / 26795 * 1000000  # parameters.jl:4
 
@@ -422,40 +422,78 @@ def _metadata_dict(sursize, surpars, simpars):
     return d
 
 
+def _is_jld_name(filename):
+    return filename.endswith(".jld")
+
+
 def _npz(filename):
     return filename if filename.endswith(".npz") else filename + ".npz"
 
 
+_TUPLE_KEYS = ("surrogate_size", "logkon_range", "logkoff_range", "logkonb_range", "reach_range")
+
+
+def _jld_values(d):
+    """the Julia types save_surrogate_metadata writes (surrogate.jl:112-123): Tuples for the size and the four
+    ranges, Int64/Float64 scalars, Vector{Float64} tsave, Array{Float64,5} FirstMoment."""
+    out = {}
+    for k, v in d.items():
+        if k in _TUPLE_KEYS:
+            a = np.asarray(v)
+            out[k] = tuple(int(x) for x in a) if a.dtype.kind in "iu" else tuple(float(x) for x in a)
+        elif isinstance(v, np.ndarray) and v.ndim == 0:
+            out[k] = v[()]
+        else:
+            out[k] = v
+    return out
+
+
+def _save(filename, d):
+    """one container per file name: `*.jld` = the reference's JLD/HDF5 layout (sprb200/jld.py), anything else the
+    .npz stand-in with the same keys (not loadable by the reference)."""
+    if _is_jld_name(filename):
+        _jld.save(filename, _jld_values(d))
+        return filename
+    np.savez(_npz(filename), **d)
+    return _npz(filename)
+
+
 def load(filename):
+    """JLD.load (surrogate.jl:73): dict of the file's variables.  Reads `.jld` files (the reference's and this
+    package's) and the .npz stand-in."""
+    if _is_jld_name(filename) or (os.path.exists(filename) and _jld.is_jld(filename)):
+        return _jld.load(filename)
     with np.load(_npz(filename)) as z:
         return {k: z[k] for k in z.files}
 
 
 def save_surrogate_metadata(filename, sursize, surpars, simpars, seed=None):
+    """surrogate.jl:112-134."""
     d = _metadata_dict(sursize, surpars, simpars)
     if seed is not None:
         d["seed"] = np.uint64(seed)
-    np.savez(_npz(filename), **d)
+    _save(filename, d)
 
 
 def save_surrogate(filename, surrogate_size, surpars, simpars, terminator=None, seed=None, device=0, devices=None):
     """surrogate.jl:151-158."""
     table = build_surrogate_serial(surrogate_size, surpars, simpars, terminator=terminator, seed=seed, device=device,
                                    devices=devices)
-    np.savez(_npz(filename), FirstMoment=table, **_metadata_dict(surrogate_size, surpars, simpars))
+    _save(filename, dict(FirstMoment=table, **_metadata_dict(surrogate_size, surpars, simpars)))
 
 
 def save_surrogate_slice(filename, surmetadata, idxstart, idxend, terminator=None, seed=None, device=0):
     """surrogate.jl:170-179."""
     sl = build_surrogate_slice(surmetadata, idxstart, idxend, terminator=terminator, seed=seed, device=device)
-    np.savez(_npz(filename), surrogate_slice=np.asfortranarray(sl), idxstart=np.int64(idxstart),
-             idxend=np.int64(idxend))
+    _save(filename, dict(surrogate_slice=np.asfortranarray(sl), idxstart=np.int64(idxstart), idxend=np.int64(idxend)))
 
 
 def merge_surrogate_slices(surmetafname, slicefilebasename, nfiles, force=False):
-    """surrogate.jl:302-332: scatters the slice columns into the table and writes it into a copy of the
-    metadata file; returns the merged file name."""
+    """surrogate.jl:302-332: scatters the slice columns into the table and writes it, with the metadata, as
+    `<slicefilebasename>_merged`; returns the merged file name.  Slice files are `<slicefilebasename>_<i>` with the
+    extension of the metadata file (`.jld` like the reference, else `.npz`)."""
     meta = load(surmetafname)
+    ext = ".jld" if _is_jld_name(surmetafname) else ".npz"
     size = tuple(int(v) for v in meta["surrogate_size"])
     P = int(np.prod(size[:4]))
     T = size[4]
@@ -463,15 +501,14 @@ def merge_surrogate_slices(surmetafname, slicefilebasename, nfiles, force=False)
     grid = _grid(surpars, size[:4])
     table = np.zeros((T, P))
     for fidx in range(1, nfiles + 1):
-        d = load(slicefilebasename + "_%d" % fidx)
+        d = load(slicefilebasename + "_%d" % fidx + ext)
         sl = np.asarray(d["surrogate_slice"])            # [T, nidx]
         _lib.merge_slice(grid, T, np.ascontiguousarray(sl.T), int(d["idxstart"]), int(d["idxend"]), table)
-    merged = _npz(slicefilebasename + "_merged")
+    merged = slicefilebasename + "_merged" + ext
     if os.path.exists(merged) and not force:
         raise FileExistsError(merged)
-    shutil.copyfile(_npz(surmetafname), merged)
     meta["FirstMoment"] = table.reshape(-1).reshape(size, order="F")
-    np.savez(merged, **meta)
+    _save(merged, meta)
     return merged
 
 

@@ -172,21 +172,23 @@ def test_generic_callback_replay(engine):
     assert all(np.array_equal(a, b) for a, b in zip(rec.rows, rec2.rows[:37]))   # same streams, chunking-independent
 
 
-def test_surrogate_builders_reference_interface(engine, tmp_path):
+@pytest.mark.parametrize("ext", ["", ".jld"])
+def test_surrogate_builders_reference_interface(engine, tmp_path, ext):
+    """ext "" = the .npz stand-in, ".jld" = the reference's own file layout (sprb200/jld.py)"""
     from sprb200 import api
     surpars = api.SurrogateParams(*RANGES)
     simpars = api.SimParams(tstop=600.0, tstop_AtoB=150.0, tsave=np.linspace(0.0, 600.0, 31), nsims=5)
     size = (2, 2, 2, 2, 31)
     table = api.build_surrogate_serial(size, surpars, simpars, terminator=api.SimNumberTerminator(), seed=5)
     assert table.shape == size and table.flags["F_CONTIGUOUS"] and np.all(table[..., 0] == 0) and table.max() <= 1.0
-    meta = str(tmp_path / "meta")
+    meta = str(tmp_path / "meta") + ext
     api.save_surrogate_metadata(meta, size, surpars, simpars, seed=5)
     base = str(tmp_path / "sl")
-    simpars_default_nsims = api.SimParams().nsims
     for f, (a, b) in enumerate(((1, 5), (6, 16)), 1):
-        api.save_surrogate_slice(base + "_%d" % f, api.load(meta), a, b,
+        api.save_surrogate_slice(base + "_%d" % f + ext, api.load(meta), a, b,
                                  terminator=api.VarianceTerminator(ssetol=0.05, minsims=3, maxsims=12))
     merged = api.merge_surrogate_slices(meta, base, 2)
+    assert merged.endswith("_merged" + (ext or ".npz"))
     sur = api.Surrogate(merged)
     assert sur.surrogate_size == size and sur.table.shape == size
     assert np.all(sur.table[..., 0] == 0) and sur.table.max() <= 1.0 and sur.table.max() > 0.1
