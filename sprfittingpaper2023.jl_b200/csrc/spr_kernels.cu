@@ -62,7 +62,16 @@ __host__ __device__ inline unsigned long long reach2_lattice(double L, double re
 //   5. degree scan + exactly-sized record from the arena, 6. compaction of the staged rows into the
 //   record.  A particle with more neighbours than the staging stride falls back to a second distance pass.
 // ------------------------------------------------------------------------------------------------
-constexpr int K2_MIN_CTAS = 4;
+#ifndef SPRB200_K2_MIN_CTAS
+#define SPRB200_K2_MIN_CTAS 4
+#endif
+#ifndef SPRB200_K2_SKIP
+#define SPRB200_K2_SKIP 1          // 0: visit all 3^DIM neighbouring cells (same rows, more candidates)
+#endif
+#ifndef SPRB200_K2_UNROLL2
+#define SPRB200_K2_UNROLL2 1       // 0: one candidate per iteration of the distance loop
+#endif
+constexpr int K2_MIN_CTAS = SPRB200_K2_MIN_CTAS;
 
 struct K2Smem {
     uint4 *p;                 // [N] cell-sorted pre-shifted lattice coordinates (x, y, z, original index)
@@ -116,38 +125,64 @@ struct RowPacker {
     }
 };
 
+// squared min-image distance on the pre-shifted lattice (32-bit wrap-around = the periodic image)
+template <int DIM>
+__device__ __forceinline__ unsigned long long lattice_dist_sq(const uint4 c, uint32_t xi, uint32_t yi, uint32_t zi) {
+    uint32_t d = c.x - xi;
+    uint32_t m = (int32_t)d < 0 ? 0u - d : d;
+    unsigned long long acc = (unsigned long long)m * m;
+    d = c.y - yi;
+    m = (int32_t)d < 0 ? 0u - d : d;
+    acc += (unsigned long long)m * m;
+    if (DIM == 3) {
+        d = c.z - zi;
+        m = (int32_t)d < 0 ? 0u - d : d;
+        acc += (unsigned long long)m * m;
+    }
+    return acc;
+}
+
 // MODE 0: count + stage (hits beyond `cap` are only counted); MODE 1: pack every hit into the record
+template <int MODE>
+__device__ __forceinline__ void take_hit(int j, uint16_t *row, int cap, RowPacker &pk, int &cnt) {
+    if (MODE == 1) pk.push((uint32_t)j);
+    else if (cnt < cap) row[cnt] = (uint16_t)j;
+    ++cnt;
+}
+
 template <int DIM, int MODE>
 __device__ __forceinline__ int scan_range(int i, uint32_t xi, uint32_t yi, uint32_t zi, int j0, int j1,
                                           const uint4 *__restrict__ p, unsigned long long r2s, uint16_t *row, int cap,
                                           RowPacker &pk, int cnt) {
+    int j = j0;
+#if SPRB200_K2_UNROLL2
+    // two candidates per iteration: both loads and both distance chains are in flight together
 #pragma unroll 1
-    for (int j = j0; j < j1; ++j) {
-        const uint4 c = p[j];
-        uint32_t d = c.x - xi;
-        uint32_t m = (int32_t)d < 0 ? 0u - d : d;
-        unsigned long long acc = (unsigned long long)m * m;
-        d = c.y - yi;
-        m = (int32_t)d < 0 ? 0u - d : d;
-        acc += (unsigned long long)m * m;
-        if (DIM == 3) {
-            d = c.z - zi;
-            m = (int32_t)d < 0 ? 0u - d : d;
-            acc += (unsigned long long)m * m;
-        }
-        if (acc <= r2s && j != i) {
-            if (MODE == 1) pk.push((uint32_t)j);
-            else if (cnt < cap) row[cnt] = (uint16_t)j;
-            ++cnt;
-        }
+    for (; j + 1 < j1; j += 2) {
+        const uint4 c0 = p[j], c1 = p[j + 1];
+        const unsigned long long a0 = lattice_dist_sq<DIM>(c0, xi, yi, zi), a1 = lattice_dist_sq<DIM>(c1, xi, yi, zi);
+        if (a0 <= r2s && j != i) take_hit<MODE>(j, row, cap, pk, cnt);
+        if (a1 <= r2s && j + 1 != i) take_hit<MODE>(j + 1, row, cap, pk, cnt);
     }
+    if (j < j1) {
+        if (lattice_dist_sq<DIM>(p[j], xi, yi, zi) <= r2s && j != i) take_hit<MODE>(j, row, cap, pk, cnt);
+    }
+#else
+#pragma unroll 1
+    for (; j < j1; ++j) {
+        if (lattice_dist_sq<DIM>(p[j], xi, yi, zi) <= r2s && j != i) take_hit<MODE>(j, row, cap, pk, cnt);
+    }
+#endif
     return cnt;
 }
 
-// all within-reach neighbours of sorted particle i, in the order of the specification
+// all within-reach neighbours of sorted particle i, in the order of the specification.
+// A neighbouring cell along an axis is only visited when the particle is within reach of the face it shares with
+// that cell (`bnd[c]` = first pre-shifted coordinate of cell c, `rmax` >= floor(sqrt(r2s))): every particle of a
+// skipped cell is farther than the reach along that axis alone, so the rows -- and their order -- are unchanged.
 template <int DIM, int MODE>
 __device__ __forceinline__ int particle_row(int i, int N, int nc, const K2Smem &s, unsigned long long r2s,
-                                            uint16_t *row, int cap, RowPacker &pk) {
+                                            uint32_t rmax, const uint32_t *bnd, uint16_t *row, int cap, RowPacker &pk) {
     const uint4 me = s.p[i];
     const uint32_t xi = me.x, yi = me.y, zi = DIM == 3 ? me.z : 0u;
     if (nc < 3) return scan_range<DIM, MODE>(i, xi, yi, zi, 0, N, s.p, r2s, row, cap, pk, 0);
@@ -155,28 +190,42 @@ __device__ __forceinline__ int particle_row(int i, int N, int nc, const K2Smem &
     const int cx = (int)__umulhi(xi, (uint32_t)nc);     // (k << 11) * nc >> 32 == (k * nc) >> 21
     const int cy = (int)__umulhi(yi, (uint32_t)nc);
     const int cz = DIM == 3 ? (int)__umulhi(zi, (uint32_t)nc) : 0;
-    // the three x-cells of a (dz,dy) row are contiguous in the sorted numbering except across the wrap
+#if SPRB200_K2_SKIP
+    const int lox = xi - bnd[cx] <= rmax ? 1 : 0, hix = bnd[cx + 1] - 1u - xi <= rmax ? 1 : 0;
+    const int loy = yi - bnd[cy] <= rmax ? 1 : 0, hiy = bnd[cy + 1] - 1u - yi <= rmax ? 1 : 0;
+    const int loz = DIM == 3 ? (zi - bnd[cz] <= rmax ? 1 : 0) : 0, hiz = DIM == 3 ? (bnd[cz + 1] - 1u - zi <= rmax ? 1 : 0) : 0;
+#else
+    const int lox = 1, hix = 1, loy = 1, hiy = 1, loz = DIM == 3 ? 1 : 0, hiz = loz;
+#endif
+    // the x-cells of a (dz,dy) row are contiguous in the sorted numbering except across the wrap
     int ax1, bx1, ax2 = 0, bx2 = 0;
     if (cx == 0) {
-        ax1 = nc - 1; bx1 = nc; ax2 = 0; bx2 = 2;
+        if (lox) {
+            ax1 = nc - 1; bx1 = nc; bx2 = 1 + hix;
+        } else {
+            ax1 = 0; bx1 = 1 + hix;
+        }
     } else if (cx == nc - 1) {
-        ax1 = nc - 2; bx1 = nc; ax2 = 0; bx2 = 1;
+        ax1 = cx - lox; bx1 = nc; bx2 = hix;
     } else {
-        ax1 = cx - 1; bx1 = cx + 2;
+        ax1 = cx - lox; bx1 = cx + 1 + hix;
     }
-    int cnt = 0;
+    const int ny = 1 + loy + hiy, nrows = ny * (1 + loz + hiz);
+    const int yy0 = cy - loy;
+    int zz = cz - loz;
+    zz = zz < 0 ? zz + nc : zz;
+    int iy = 0, cnt = 0;
 #pragma unroll 1
-    for (int dz = (DIM == 3 ? -1 : 0); dz <= (DIM == 3 ? 1 : 0); ++dz) {
-        int zz = cz + dz;
-        zz = zz < 0 ? zz + nc : (zz >= nc ? zz - nc : zz);
-#pragma unroll 1
-        for (int dy = -1; dy <= 1; ++dy) {
-            int yy = cy + dy;
-            yy = yy < 0 ? yy + nc : (yy >= nc ? yy - nc : yy);
-            const int rb = (zz * nc + yy) * nc;
-            cnt = scan_range<DIM, MODE>(i, xi, yi, zi, (int)cs1[rb + ax1], (int)cs1[rb + bx1], s.p, r2s, row, cap, pk, cnt);
-            if (bx2 > ax2)
-                cnt = scan_range<DIM, MODE>(i, xi, yi, zi, (int)cs1[rb + ax2], (int)cs1[rb + bx2], s.p, r2s, row, cap, pk, cnt);
+    for (int r = 0; r < nrows; ++r) {                   // (dz, dy) ascending, like the full 3 x 3 sweep
+        int yy = yy0 + iy;
+        yy = yy < 0 ? yy + nc : (yy >= nc ? yy - nc : yy);
+        const int rb = (zz * nc + yy) * nc;
+        cnt = scan_range<DIM, MODE>(i, xi, yi, zi, (int)cs1[rb + ax1], (int)cs1[rb + bx1], s.p, r2s, row, cap, pk, cnt);
+        if (bx2 > ax2)
+            cnt = scan_range<DIM, MODE>(i, xi, yi, zi, (int)cs1[rb + ax2], (int)cs1[rb + bx2], s.p, r2s, row, cap, pk, cnt);
+        if (++iy == ny) {
+            iy = 0;
+            zz = zz + 1 >= nc ? 0 : zz + 1;
         }
     }
     return cnt;
@@ -195,6 +244,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(cons
     __shared__ long long s_ticket;
     __shared__ unsigned long long s_base;
     __shared__ unsigned int s_maxdeg;
+    __shared__ uint32_t s_bnd[40];             // [nc+1] first pre-shifted coordinate of every cell along an axis (nc <= 32)
     const int N = a.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     K2Smem s;
     s.p = reinterpret_cast<uint4 *>(smem_raw);
@@ -227,9 +277,14 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(cons
         const unsigned long long r2lat = reach2_lattice(a.L, reach);
         const unsigned long long r2s = r2lat >= (3ULL << 40) ? (3ULL << 62) : (r2lat << 22);
         const int cap = min(a.stage_cap, k2_stage_cap(N, DIM, a.L, reach));
+        // >= floor(sqrt(r2s)) (the double square root is within 1 of it), saturated: no cell is skipped then
+        const double rq = sqrt((double)r2s) + 2.0;
+        const uint32_t rmax = rq >= 4294967295.0 ? 0xffffffffu : (uint32_t)rq;
 
         // ---- 1. positions, cell counts (kept at cs[c+2]) and arrival ranks
         for (int c = tid; c < ncell + 2; c += K2_THREADS) s.cs[c] = 0u;
+        // ceil(c 2^32 / nc) mod 2^32: cell c holds the coordinates [bnd[c], bnd[c+1]) (bnd[nc] wraps to 0)
+        if (tid <= nc && nc >= 3) s_bnd[tid] = (uint32_t)((((unsigned long long)tid << 32) + (unsigned long long)(nc - 1)) / (unsigned long long)nc);
         __syncthreads();
         for (int i = tid; i < N; i += K2_THREADS) {
             const u32x4 r = philox4x32_10((uint32_t)i, STREAM_POSITIONS, rep, pidx, a.seed_lo, a.seed_hi);
@@ -280,7 +335,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(cons
         unsigned int mydeg = 0u;
         for (int i = tid; i < N; i += K2_THREADS) {
             RowPacker none{nullptr, 0u, 0, 1, 16};
-            const int c = particle_row<DIM, 0>(i, N, nc, s, r2s, stage + (size_t)i * (size_t)a.stage_cap, cap, none);
+            const int c = particle_row<DIM, 0>(i, N, nc, s, r2s, rmax, s_bnd, stage + (size_t)i * (size_t)a.stage_cap, cap, none);
             s.seg[i] = (uint16_t)c;                       // degree (seg is dead after the sort)
             s.off[i + 1] = (uint32_t)((c + a.epw - 1) / a.epw);   // words of the packed row
             mydeg = max(mydeg, (unsigned int)c);
@@ -339,7 +394,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(cons
         } else {
             for (int i = tid; i < N; i += K2_THREADS) {
                 RowPacker pk{gw + s.off[i], 0u, 0, a.epw, a.eb};
-                particle_row<DIM, 1>(i, N, nc, s, r2s, nullptr, 0, pk);
+                particle_row<DIM, 1>(i, N, nc, s, r2s, rmax, s_bnd, nullptr, 0, pk);
                 pk.flush();
             }
         }
