@@ -174,7 +174,8 @@ size_t record_estimate(int N, int DIM, double L, double reach, double scale) {
     return record_bytes(N, (unsigned long long)std::ceil(words));
 }
 
-// rough SSA event count of one trajectory (only used to start expensive points first)
+// rough SSA event count of one trajectory: the ranking that starts expensive points first inside one GPU's share
+// (10^4 evaluations per C2 build sit on the timed path; the deal between GPUs uses events_estimate below)
 double cost_estimate(const PointDev &p, int N, int DIM, double L, double tstop, double toff) {
     const double PI = 3.14159265358979323846;
     const double ta = std::min(std::max(toff, 0.0), tstop), td = tstop - ta;
@@ -187,6 +188,126 @@ double cost_estimate(const PointDev &p, int N, int DIM, double L, double tstop, 
     const double pre = (konb + koff) > 0 ? konb / (konb + koff) : 0.0; // re-formation probability
     ev += N * std::min(1.0, deg) * bound * 2.0 * koff * tstop * pre * (1.0 + pre * 4.0);
     return (ev + 600.0) * (1.0 + deg / 32.0);
+}
+
+// ---- expected SSA events of one trajectory from the mean-field kinetics of the four channels ----------------
+// (what the multi-GPU deal balances; the in-rank ordering above only needs a ranking and keeps the cheap formula.)
+// Fractions a, b, c of the particles in states A, B and in a complex obey
+//     da/dt = -kon a + koff (1 - a) - p a b,     db/dt = kon a + koff (1 - a) - 2 koff b - p a b,     c = 1 - a - b
+// with p = konb x (neighbours within reach); the event rate per particle is kon a + koff (1 - a) + p a b.  Particles
+// without any neighbour (a fraction exp(-degree) of a uniform configuration) only flip A <-> B (closed form); the others
+// see the conditional mean degree.  On 80,000 points of the C2 ranges this is within 2 % of the events the kernels
+// execute in every degree class, 1 % - 99 % quantiles of true/estimate 0.87 - 1.14 (tests/tools/cost_model_check.py:
+// oracle/spr_mirror.c counts the events bit for bit), and the slowest of 8 ranks gets +0.1 % of the mean instead
+// of +1.6 % with the cheap formula.
+struct OdeGrid {
+    // geometric steps h0 q^k, k < NSTEP, that sum to the phase length
+    static constexpr int NSTEP = 24;
+    double h0 = 0.0, q = 1.0;
+    explicit OdeGrid(double dur) {
+        if (!(dur > 0.0)) return;
+        h0 = std::min(1e-3, dur / NSTEP);
+        if (h0 * NSTEP >= dur) { h0 = dur / NSTEP; return; }
+        double lo = 1.0, hi = 16.0;
+        for (int it = 0; it < 60; ++it) {
+            const double m = 0.5 * (lo + hi);
+            const double sum = h0 * (std::pow(m, NSTEP) - 1.0) / (m - 1.0);
+            if (sum > dur) hi = m; else lo = m;
+        }
+        q = 0.5 * (lo + hi);
+    }
+};
+
+struct PairOde {
+    double k1, k2, p;
+    double rate(double a, double b) const { return k1 * a + k2 * (1.0 - a) + p * a * b; }
+    // one backward-Euler step (two Newton iterations from the old state; the Jacobian's determinant is >= 1)
+    void step(double a, double b, double h, double *ao, double *bo) const {
+        double an = a, bn = b;
+        for (int it = 0; it < 2; ++it) {
+            const double pab = p * an * bn;
+            const double F1 = an - a - h * (-k1 * an + k2 * (1.0 - an) - pab);
+            const double F2 = bn - b - h * (k1 * an + k2 * (1.0 - an) - 2.0 * k2 * bn - pab);
+            const double J11 = 1.0 + h * (k1 + k2 + p * bn), J12 = h * p * an;
+            const double J21 = -h * (k1 - k2 - p * bn), J22 = 1.0 + h * (2.0 * k2 + p * an);
+            const double det = J11 * J22 - J12 * J21;
+            an = std::min(1.0, std::max(0.0, an - (F1 * J22 - F2 * J12) / det));
+            bn = std::min(1.0, std::max(0.0, bn - (J11 * F2 - J21 * F1) / det));
+        }
+        *ao = an; *bo = bn;
+    }
+    // events per particle over one phase; Richardson extrapolation of the step (second order, still damping the
+    // fast modes), Simpson's rule for the rate
+    double phase(const OdeGrid &g, double *a, double *b) const {
+        double E = 0.0, h = g.h0;
+        if (!(h > 0.0)) return 0.0;
+        for (int s = 0; s < OdeGrid::NSTEP; ++s) {
+            double a1, b1, am, bm, a2, b2;
+            step(*a, *b, h, &a1, &b1);
+            step(*a, *b, 0.5 * h, &am, &bm);
+            step(am, bm, 0.5 * h, &a2, &b2);
+            const double ae = std::min(1.0, std::max(0.0, 2.0 * a2 - a1)), be = std::min(1.0, std::max(0.0, 2.0 * b2 - b1));
+            E += h * (rate(*a, *b) + 4.0 * rate(am, bm) + rate(ae, be)) / 6.0;
+            *a = ae; *b = be;
+            h *= g.q;
+        }
+        return E;
+    }
+};
+
+double events_estimate(const PointDev &p, int N, int DIM, double L, double tstop, double toff, const OdeGrid &gon,
+                       const OdeGrid &goff) {
+    const double PI = 3.14159265358979323846;
+    const double ta = std::min(std::max(toff, 0.0), tstop), td = tstop - ta;
+    const double k1 = p.kon_eff, k2 = p.koff;
+    double frac = DIM == 3 ? (4.0 / 3.0) * PI * p.reach * p.reach * p.reach / (L * L * L) : PI * p.reach * p.reach / (L * L);
+    const double deg = std::min((double)(N - 1), (double)(N - 1) * std::min(frac, 1.0));
+    const double phi = -std::expm1(-deg);                    // particles with at least one neighbour
+    // isolated particles: a' = -k1 a + k2 (1 - a), rate k2 + (k1 - k2) a
+    double E0 = 0.0, a_off = 1.0;
+    const double lam = k1 + k2;
+    if (lam > 0.0 && ta > 0.0) {
+        const double astar = k2 / lam, rel = -std::expm1(-lam * ta) / lam;
+        E0 = k2 * ta + (k1 - k2) * (astar * ta + (1.0 - astar) * rel);
+        a_off = astar + (1.0 - astar) * std::exp(-lam * ta);
+    }
+    E0 += (1.0 - a_off) * -std::expm1(-k2 * td);
+    double E1 = E0;
+    if (phi > 0.0 && p.konb > 0.0) {
+        PairOde ode{k1, k2, p.konb * deg / phi};
+        double a = 1.0, b = 0.0;
+        E1 = ode.phase(gon, &a, &b);
+        ode.k1 = 0.0;
+        E1 += ode.phase(goff, &a, &b);
+    }
+    const double ev = (double)N * ((1.0 - phi) * E0 + phi * E1);
+    return std::isfinite(ev) && ev >= 0.0 ? ev : -1.0;
+}
+
+// cost of one replicate as the deal sees it: events (+ the save slots) x neighbour work per event
+double deal_cost(const PointDev &p, int N, int DIM, double L, double tstop, double toff, const OdeGrid &gon, const OdeGrid &goff) {
+    const double ev = events_estimate(p, N, DIM, L, tstop, toff, gon, goff);
+    if (ev < 0.0) return cost_estimate(p, N, DIM, L, tstop, toff);
+    const double PI = 3.14159265358979323846;
+    double frac = DIM == 3 ? (4.0 / 3.0) * PI * p.reach * p.reach * p.reach / (L * L * L) : PI * p.reach * p.reach / (L * L);
+    const double deg = std::min((double)(N - 1), (double)(N - 1) * std::min(frac, 1.0));
+    return (ev + 600.0) * (1.0 + deg / 32.0);
+}
+
+// deal_cost of many points on the host threads (a paper-scale grid has 1.5 million of them)
+template <typename GetPoint>
+void deal_costs(int64_t npts, const SprSim *sim, GetPoint get, double *out) {
+    const double ta = std::min(std::max(sim->tstop_AtoB, 0.0), sim->tstop);
+    const OdeGrid gon(ta), goff(sim->tstop - ta);
+    auto work = [&](int64_t b, int64_t e) {
+        for (int64_t k = b; k < e; ++k) out[k] = deal_cost(get(k), sim->N, sim->DIM, sim->L, sim->tstop, sim->tstop_AtoB, gon, goff);
+    };
+    int nth = (int)std::min<int64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), npts / 2048 + 1);
+    if (nth <= 1) { work(0, npts); return; }
+    std::vector<std::thread> th;
+    const int64_t per = (npts + nth - 1) / nth;
+    for (int t = 0; t < nth; ++t) th.emplace_back(work, std::min<int64_t>(npts, t * per), std::min<int64_t>(npts, (t + 1) * per));
+    for (auto &t : th) t.join();
 }
 
 struct RunPlan {
@@ -742,15 +863,53 @@ double replicate_estimate(const PointDev &p, int DIM, const SprSim *sim, const S
     return std::min((double)run->maxsims, std::max((double)run->minsims, n));
 }
 
+// the last deal is kept: a build asks for it once per call (twice through sprb200_deal_indices), and a caller that
+// repeats a build asks for the same one again
+struct DealMemo {
+    std::mutex mu;
+    std::vector<unsigned char> key;
+    std::vector<std::vector<int64_t>> deal;
+} g_deal_memo;
+
+std::vector<unsigned char> deal_key(const SprGrid *grid, const SprSim *sim, const SprRun *run, int nranks) {
+    std::vector<unsigned char> k;
+    auto put = [&](const void *p, size_t n) { k.insert(k.end(), (const unsigned char *)p, (const unsigned char *)p + n); };
+    put(grid, sizeof(*grid));
+    put(&sim->N, sizeof(sim->N)); put(&sim->DIM, sizeof(sim->DIM)); put(&sim->L, sizeof(sim->L));
+    put(&sim->tstop, sizeof(sim->tstop)); put(&sim->tstop_AtoB, sizeof(sim->tstop_AtoB));
+    double t1 = -1.0;                                         // what replicate_estimate reads of tsave
+    if (sim->tsave)
+        for (int s = 0; s < sim->T; ++s)
+            if (sim->tsave[s] > 0.0) { t1 = sim->tsave[s]; break; }
+    put(&t1, sizeof(t1));
+    const int variance = run && run->term_kind == SPRB200_TERM_VARIANCE ? 1 : 0;
+    put(&variance, sizeof(variance));
+    if (variance) { put(&run->ssetol, sizeof(run->ssetol)); put(&run->minsims, sizeof(run->minsims)); put(&run->maxsims, sizeof(run->maxsims)); }
+    put(&nranks, sizeof(nranks));
+    return k;
+}
+
 int deal_points(const SprGrid *grid, const SprSim *sim, const SprRun *run, int nranks, std::vector<std::vector<int64_t>> *out) {
     int64_t P = 0;
     if (grid_total(grid, &P) || nranks < 1) return SPRB200_ERR_BAD_ARG;
+    if (nranks == 1) {                                        // nothing to balance
+        out->assign(1, std::vector<int64_t>((size_t)P));
+        for (int64_t i = 0; i < P; ++i) (*out)[0][(size_t)i] = i + 1;
+        return SPRB200_OK;
+    }
+    const std::vector<unsigned char> key = deal_key(grid, sim, run, nranks);
+    std::lock_guard<std::mutex> lk(g_deal_memo.mu);
+    if (key == g_deal_memo.key) {
+        *out = g_deal_memo.deal;
+        return SPRB200_OK;
+    }
+    std::vector<double> cost((size_t)P);
+    deal_costs(P, sim, [&](int64_t i) { PointDev p; grid_point(grid, i, &p); return p; }, cost.data());
     std::vector<std::pair<double, int64_t>> keyed((size_t)P);
     for (int64_t i = 0; i < P; ++i) {
         PointDev p;
         grid_point(grid, i, &p);
-        keyed[(size_t)i] = std::make_pair(-cost_estimate(p, sim->N, sim->DIM, sim->L, sim->tstop, sim->tstop_AtoB) *
-                                              replicate_estimate(p, sim->DIM, sim, run), i);
+        keyed[(size_t)i] = std::make_pair(-cost[(size_t)i] * replicate_estimate(p, sim->DIM, sim, run), i);
     }
     std::sort(keyed.begin(), keyed.end());
     out->assign((size_t)nranks, std::vector<int64_t>());
@@ -761,6 +920,8 @@ int deal_points(const SprGrid *grid, const SprSim *sim, const SprRun *run, int n
         (*out)[(size_t)r].push_back(keyed[(size_t)k].second + 1);   // 1-based linear index
     }
     for (auto &v : *out) std::sort(v.begin(), v.end());
+    g_deal_memo.key = key;
+    g_deal_memo.deal = *out;
     return SPRB200_OK;
 }
 
@@ -915,10 +1076,7 @@ int sprb200_last_kernel_ms(sprb200_handle h, double *table_ms, double *traj_ms) 
 int sprb200_estimate_cost(const SprSim *sim, const SprPoint *pts, int64_t npts, double *cost_out) {
     if (!sim || !pts || !cost_out || npts < 0 || sim->N < 1 || (sim->DIM != 2 && sim->DIM != 3) || !(sim->L > 0.0))
         return SPRB200_ERR_BAD_ARG;
-    for (int64_t k = 0; k < npts; ++k) {
-        const PointDev p{pts[k].kon_eff, pts[k].koff, pts[k].konb, pts[k].reach};
-        cost_out[k] = cost_estimate(p, sim->N, sim->DIM, sim->L, sim->tstop, sim->tstop_AtoB);
-    }
+    deal_costs(npts, sim, [&](int64_t k) { return PointDev{pts[k].kon_eff, pts[k].koff, pts[k].konb, pts[k].reach}; }, cost_out);
     return SPRB200_OK;
 }
 

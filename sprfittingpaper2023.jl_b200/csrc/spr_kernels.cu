@@ -66,7 +66,13 @@ __host__ __device__ inline unsigned long long reach2_lattice(double L, double re
 #define SPRB200_K2_MIN_CTAS 6
 #endif
 #ifndef SPRB200_K2_SKIP
-#define SPRB200_K2_SKIP 2          // 0: visit all 3^DIM neighbouring cells; 1: per-axis skip; 2: per-row skip (particle_row)
+#define SPRB200_K2_SKIP 1          // 0: visit all 3^DIM neighbouring cells (same rows, more candidates)
+#endif
+#ifndef SPRB200_K2_UNROLL2
+#define SPRB200_K2_UNROLL2 1       // 0: one candidate per iteration of the distance loop
+#endif
+#ifndef SPRB200_K2_SIGNED
+#define SPRB200_K2_SIGNED 1        // 0: |d| and an unsigned square (three more instructions per candidate)
 #endif
 constexpr int K2_MIN_CTAS = SPRB200_K2_MIN_CTAS;
 
@@ -126,6 +132,7 @@ struct RowPacker {
 // IS the periodic image, and its signed 64-bit square the exact square (|d| <= 2^31)
 template <int DIM>
 __device__ __forceinline__ unsigned long long lattice_dist_sq(const uint4 c, uint32_t xi, uint32_t yi, uint32_t zi) {
+#if SPRB200_K2_SIGNED
     const int32_t dx = (int32_t)(c.x - xi), dy = (int32_t)(c.y - yi);
     long long acc = (long long)dx * dx + (long long)dy * dy;
     if (DIM == 3) {
@@ -133,110 +140,71 @@ __device__ __forceinline__ unsigned long long lattice_dist_sq(const uint4 c, uin
         acc += (long long)dz * dz;
     }
     return (unsigned long long)acc;
+#else
+    uint32_t d = c.x - xi;
+    uint32_t m = (int32_t)d < 0 ? 0u - d : d;
+    unsigned long long acc = (unsigned long long)m * m;
+    d = c.y - yi;
+    m = (int32_t)d < 0 ? 0u - d : d;
+    acc += (unsigned long long)m * m;
+    if (DIM == 3) {
+        d = c.z - zi;
+        m = (int32_t)d < 0 ? 0u - d : d;
+        acc += (unsigned long long)m * m;
+    }
+    return acc;
+#endif
 }
 
-// One contiguous range [j0, j1) of candidates.  The candidate loop only collects hit bits (two predicated
-// instructions per candidate, no branch: the warp does not leave the loop whenever one of its lanes has a hit);
-// the hits of up to 32 candidates are emitted afterwards, in index order.
-// MODE 0: count + stage at row[cnt] (positions >= cap are only counted; the particle itself is staged like a
-// neighbour and dropped when the rows are packed, which takes the `j != i` test out of the candidate loop);
-// MODE 1: pack every hit into the record.
+// MODE 0: count + stage (hits beyond `cap` are only counted); MODE 1: pack every hit into the record
+template <int MODE>
+__device__ __forceinline__ void take_hit(int j, uint16_t *row, int cap, RowPacker &pk, int &cnt) {
+    if (MODE == 1) pk.push((uint32_t)j);
+    else if (cnt < cap) row[cnt] = (uint16_t)j;
+    ++cnt;
+}
+
 template <int DIM, int MODE>
 __device__ __forceinline__ int scan_range(int i, uint32_t xi, uint32_t yi, uint32_t zi, int j0, int j1,
                                           const uint4 *__restrict__ p, unsigned long long r2s, uint16_t *row, int cap,
                                           RowPacker &pk, int cnt) {
+    int j = j0;
+#if SPRB200_K2_UNROLL2
+    // two candidates per iteration: both loads and both distance chains are in flight together
 #pragma unroll 1
-    for (int jb = j0; jb < j1; jb += 32) {
-        const int n = min(32, j1 - jb);
-        uint32_t mask = 0u;                  // after k candidates: their hit bits in the top k bits, oldest lowest
-        int k = 0;
-#pragma unroll 1
-        for (; k + 1 < n; k += 2) {          // two candidates per iteration: both loads and distance chains in flight
-            const uint4 c0 = p[jb + k], c1 = p[jb + k + 1];
-            const unsigned long long a0 = lattice_dist_sq<DIM>(c0, xi, yi, zi), a1 = lattice_dist_sq<DIM>(c1, xi, yi, zi);
-            mask >>= 2;
-            if (a0 <= r2s) mask |= 0x40000000u;
-            if (a1 <= r2s) mask |= 0x80000000u;
-        }
-        if (k < n) {
-            mask >>= 1;
-            if (lattice_dist_sq<DIM>(p[jb + k], xi, yi, zi) <= r2s) mask |= 0x80000000u;
-        }
-        mask >>= 32 - n;                     // n >= 1: bit b = candidate jb + b
-        while (mask) {
-            const int j = jb + __ffs((int)mask) - 1;
-            mask &= mask - 1u;
-            if (MODE == 1) {
-                if (j != i) {
-                    pk.push((uint32_t)j);
-                    ++cnt;
-                }
-            } else {
-                if (cnt < cap) row[(uint32_t)cnt] = (uint16_t)j;
-                ++cnt;
-            }
-        }
+    for (; j + 1 < j1; j += 2) {
+        const uint4 c0 = p[j], c1 = p[j + 1];
+        const unsigned long long a0 = lattice_dist_sq<DIM>(c0, xi, yi, zi), a1 = lattice_dist_sq<DIM>(c1, xi, yi, zi);
+        if (a0 <= r2s && j != i) take_hit<MODE>(j, row, cap, pk, cnt);
+        if (a1 <= r2s && j + 1 != i) take_hit<MODE>(j + 1, row, cap, pk, cnt);
     }
+    if (j < j1) {
+        if (lattice_dist_sq<DIM>(p[j], xi, yi, zi) <= r2s && j != i) take_hit<MODE>(j, row, cap, pk, cnt);
+    }
+#else
+#pragma unroll 1
+    for (; j < j1; ++j) {
+        if (lattice_dist_sq<DIM>(p[j], xi, yi, zi) <= r2s && j != i) take_hit<MODE>(j, row, cap, pk, cnt);
+    }
+#endif
     return cnt;
 }
 
-// all within-reach neighbours of sorted particle i (MODE 0: and i itself), in the order of the specification.
-// Cells are only visited when they can hold a neighbour: with g = the distance from the particle to the face of
-// its own cell towards a neighbouring cell (`bnd[c]` = first pre-shifted coordinate of cell c), every particle of
-// that neighbouring cell is farther than g along that axis.  SPRB200_K2_SKIP 1: a cell is skipped when one of its
-// g exceeds the reach; 2: when the sum of the squares of its g does (a (dz,dy) row of cells is dropped, or
-// shortened in x, by what is left of reach^2 after its y and z gaps).  The rows and their order are unchanged.
+// all within-reach neighbours of sorted particle i, in the order of the specification.
+// A neighbouring cell along an axis is only visited when the particle is within reach of the face it shares with
+// that cell (`bnd[c]` = first pre-shifted coordinate of cell c, `rmax` >= floor(sqrt(r2s))): every particle of a
+// skipped cell is farther than the reach along that axis alone, so the rows -- and their order -- are unchanged.
 template <int DIM, int MODE>
 __device__ __forceinline__ int particle_row(int i, int N, int nc, const K2Smem &s, unsigned long long r2s,
-                                            uint32_t rmax, const uint32_t *bnd, uint16_t *row, int cnt0, int cap, RowPacker &pk) {
+                                            uint32_t rmax, const uint32_t *bnd, uint16_t *row, int cap, RowPacker &pk) {
     const uint4 me = s.p[i];
     const uint32_t xi = me.x, yi = me.y, zi = DIM == 3 ? me.z : 0u;
-    if (nc < 3) return scan_range<DIM, MODE>(i, xi, yi, zi, 0, N, s.p, r2s, row, cap, pk, cnt0);
+    if (nc < 3) return scan_range<DIM, MODE>(i, xi, yi, zi, 0, N, s.p, r2s, row, cap, pk, 0);
     const uint32_t *cs1 = s.cs + 1;                     // cs1[c] = first sorted index of cell c
     const int cx = (int)__umulhi(xi, (uint32_t)nc);     // (k << 11) * nc >> 32 == (k * nc) >> 21
     const int cy = (int)__umulhi(yi, (uint32_t)nc);
     const int cz = DIM == 3 ? (int)__umulhi(zi, (uint32_t)nc) : 0;
-    int cnt = cnt0;
-#if SPRB200_K2_SKIP == 2
-    // gaps are smaller than a cell (< 2^32 / 3): their squares and the sum of three fit 64 bits
-    const uint32_t gxl = xi - bnd[cx], gxh = bnd[cx + 1] - 1u - xi;
-    const uint32_t gyl = yi - bnd[cy], gyh = bnd[cy + 1] - 1u - yi;
-    const uint32_t gzl = DIM == 3 ? zi - bnd[cz] : 0u, gzh = DIM == 3 ? bnd[cz + 1] - 1u - zi : 0u;
-    const unsigned long long qxl = (unsigned long long)gxl * gxl, qxh = (unsigned long long)gxh * gxh;
-    const unsigned long long qyl = (unsigned long long)gyl * gyl, qyh = (unsigned long long)gyh * gyh;
-    const unsigned long long qzl = (unsigned long long)gzl * gzl, qzh = (unsigned long long)gzh * gzh;
-    (void)rmax;
-#pragma unroll 1
-    for (int r = 0; r < (DIM == 3 ? 9 : 3); ++r) {      // (dz, dy) ascending
-        const int dz = DIM == 3 ? (r >= 6 ? 1 : (r >= 3 ? 0 : -1)) : 0;
-        const int dy = DIM == 3 ? r - 3 * (dz + 1) - 1 : r - 1;
-        const unsigned long long q = (dy < 0 ? qyl : (dy > 0 ? qyh : 0ULL)) + (dz < 0 ? qzl : (dz > 0 ? qzh : 0ULL));
-        if (q > r2s) continue;
-        const unsigned long long rem = r2s - q;
-        const int lox = qxl <= rem ? 1 : 0, hix = qxh <= rem ? 1 : 0;
-        int zz = cz + dz, yy = cy + dy;
-        zz = zz < 0 ? zz + nc : (zz >= nc ? zz - nc : zz);
-        yy = yy < 0 ? yy + nc : (yy >= nc ? yy - nc : yy);
-        const int rb = (zz * nc + yy) * nc;
-        // the x-cells of a (dz,dy) row are contiguous in the sorted numbering except across the wrap
-        int ax1, bx1, ax2 = 0, bx2 = 0;
-        if (cx == 0) {
-            if (lox) {
-                ax1 = nc - 1; bx1 = nc; bx2 = 1 + hix;
-            } else {
-                ax1 = 0; bx1 = 1 + hix;
-            }
-        } else if (cx == nc - 1) {
-            ax1 = cx - lox; bx1 = nc; bx2 = hix;
-        } else {
-            ax1 = cx - lox; bx1 = cx + 1 + hix;
-        }
-        cnt = scan_range<DIM, MODE>(i, xi, yi, zi, (int)cs1[rb + ax1], (int)cs1[rb + bx1], s.p, r2s, row, cap, pk, cnt);
-        if (bx2 > ax2)
-            cnt = scan_range<DIM, MODE>(i, xi, yi, zi, (int)cs1[rb + ax2], (int)cs1[rb + bx2], s.p, r2s, row, cap, pk, cnt);
-    }
-#else
-#if SPRB200_K2_SKIP == 1
+#if SPRB200_K2_SKIP
     const int lox = xi - bnd[cx] <= rmax ? 1 : 0, hix = bnd[cx + 1] - 1u - xi <= rmax ? 1 : 0;
     const int loy = yi - bnd[cy] <= rmax ? 1 : 0, hiy = bnd[cy + 1] - 1u - yi <= rmax ? 1 : 0;
     const int loz = DIM == 3 ? (zi - bnd[cz] <= rmax ? 1 : 0) : 0, hiz = DIM == 3 ? (bnd[cz + 1] - 1u - zi <= rmax ? 1 : 0) : 0;
@@ -260,7 +228,7 @@ __device__ __forceinline__ int particle_row(int i, int N, int nc, const K2Smem &
     const int yy0 = cy - loy;
     int zz = cz - loz;
     zz = zz < 0 ? zz + nc : zz;
-    int iy = 0;
+    int iy = 0, cnt = 0;
 #pragma unroll 1
     for (int r = 0; r < nrows; ++r) {                   // (dz, dy) ascending, like the full 3 x 3 sweep
         int yy = yy0 + iy;
@@ -274,7 +242,6 @@ __device__ __forceinline__ int particle_row(int i, int N, int nc, const K2Smem &
             zz = zz + 1 >= nc ? 0 : zz + 1;
         }
     }
-#endif
     return cnt;
 }
 
@@ -382,10 +349,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(cons
         unsigned int mydeg = 0u;
         for (int i = tid; i < N; i += K2_THREADS) {
             RowPacker none{nullptr, 0u, 0, 1, 16};
-            // hits include the particle itself: degree = hits - 1
-            // staged at stage[i * stage_cap ...): the running position is a 32-bit index into the CTA's staging area
-            const int st0 = i * a.stage_cap;
-            const int c = particle_row<DIM, 0>(i, N, nc, s, r2s, rmax, s_bnd, stage, st0, st0 + cap, none) - st0 - 1;
+            const int c = particle_row<DIM, 0>(i, N, nc, s, r2s, rmax, s_bnd, stage + (size_t)i * (size_t)a.stage_cap, cap, none);
             s.seg[i] = (uint16_t)c;                       // degree (seg is dead after the sort)
             s.off[i + 1] = (uint32_t)((c + a.epw - 1) / a.epw);   // words of the packed row
             mydeg = max(mydeg, (unsigned int)c);
@@ -433,21 +397,18 @@ __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS) spr_table_kernel(cons
         uint32_t *goff = reinterpret_cast<uint32_t *>(a.arena + at);
         uint32_t *gw = reinterpret_cast<uint32_t *>(a.arena + at + (((size_t)(N + 1) * 4 + 15) & ~(size_t)15));
         for (int i = tid; i <= N; i += K2_THREADS) goff[i] = s.off[i];
-        if ((int)s_maxdeg < cap) {                         // every staged row (neighbours + the particle itself) fitted
+        if ((int)s_maxdeg <= cap) {
             for (int i = tid; i < N; i += K2_THREADS) {
                 const int dg = (int)s.seg[i];
                 const uint16_t *src = stage + (size_t)i * (size_t)a.stage_cap;
                 RowPacker pk{gw + s.off[i], 0u, 0, a.epw, a.eb};
-                for (int k = 0; k <= dg; ++k) {
-                    const uint32_t j = (uint32_t)src[k];
-                    if (j != (uint32_t)i) pk.push(j);
-                }
+                for (int k = 0; k < dg; ++k) pk.push((uint32_t)src[k]);
                 pk.flush();
             }
         } else {
             for (int i = tid; i < N; i += K2_THREADS) {
                 RowPacker pk{gw + s.off[i], 0u, 0, a.epw, a.eb};
-                particle_row<DIM, 1>(i, N, nc, s, r2s, rmax, s_bnd, nullptr, 0, 0, pk);
+                particle_row<DIM, 1>(i, N, nc, s, r2s, rmax, s_bnd, nullptr, 0, pk);
                 pk.flush();
             }
         }

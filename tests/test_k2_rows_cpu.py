@@ -3,8 +3,8 @@
 The device functions are extracted verbatim from the .cu file (tests/c/k2_rows_harness.cpp supplies `uint4`,
 `__umulhi`, `__ffs`) and run against an O(N^2) scan of the same lattice positions: DIM 2 and 3, reach from 0 to
 beyond the box (all-pairs path), coincident particles and particles on the box faces, staging rows that overflow.
-Every cell-skipping level (SPRB200_K2_SKIP 0 = all 3^DIM cells, 1 = per axis, 2 = per row of cells) must give the
-same neighbours in the same order: skipping is an optimisation, not a change of the specification
+Every build variant (SPRB200_K2_SKIP 0 = all 3^DIM cells / 1 = per-axis cell skipping, with and without the signed
+squares and the two-candidate loop) must give the same neighbours in the same order: skipping is an optimisation, not a change of the specification
 (forward_simulator.jl:37-61: `periodic_dist_sq <= reach^2`)."""
 import os
 import subprocess
@@ -23,13 +23,15 @@ def _extract(dst):
         f.write(k2 + "\n" + body)
 
 
-def test_particle_rows_match_all_pairs_scan_at_every_skip_level(tmp_path):
+def test_particle_rows_match_all_pairs_scan_in_every_variant(tmp_path):
     d = str(tmp_path)
     _extract(d)
     outs = []
-    for level in (0, 1, 2):
-        exe = os.path.join(d, "h%d" % level)
-        subprocess.run(["g++", "-O1", "-std=c++17", "-I", d, "-DSPRB200_K2_SKIP=%d" % level, "-o", exe,
+    for n, flags in enumerate((("-DSPRB200_K2_SKIP=0", "-DSPRB200_K2_SIGNED=0", "-DSPRB200_K2_UNROLL2=0"),
+                               ("-DSPRB200_K2_SKIP=1", "-DSPRB200_K2_SIGNED=0", "-DSPRB200_K2_UNROLL2=1"),
+                               ("-DSPRB200_K2_SKIP=1", "-DSPRB200_K2_SIGNED=1", "-DSPRB200_K2_UNROLL2=1"))):
+        exe = os.path.join(d, "h%d" % n)
+        subprocess.run(["g++", "-O1", "-std=c++17", "-I", d, *flags, "-o", exe,
                         os.path.join(ROOT, "tests", "c", "k2_rows_harness.cpp")], check=True)
         r = subprocess.run([exe], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-2000:]
