@@ -146,9 +146,10 @@ int sprb200_last_kernel_ms(sprb200_handle h, double *table_ms, double *traj_ms);
  * 4 CTAs per SM.  SPRB200_TMEM=0 in the environment switches that variant off.) */
 int sprb200_traj_layout(int32_t N, int32_t wide_state, int32_t wide_offsets, int32_t out[4]);
 
-/* Rough relative cost (SSA events x neighbour work of one replicate) of each point: the ordering the library
- * itself uses to start expensive points first.  Device-free; callers use it to deal points to ranks so
- * that every GPU gets the same cost mix (bench.py).  sim->tsave may be NULL here. */
+/* Relative cost (expected SSA events x neighbour work of one replicate) of each point, the figure the library's own
+ * multi-GPU deal (sprb200_deal_indices) balances on grids of up to 400,000 points: the events come from the mean-field
+ * kinetics of the four reaction channels (a two-variable ODE per point, about 3 us; within a few per cent of the
+ * executed events over the C2 ranges, tests/tools/cost_model_check.py).  Device-free; sim->tsave may be NULL here. */
 int sprb200_estimate_cost(const SprSim *sim, const SprPoint *pts, int64_t npts, double *cost_out);
 
 /* ---- helpers --------------------------------------------------------------------------- */

@@ -202,7 +202,7 @@ double cost_estimate(const PointDev &p, int N, int DIM, double L, double tstop, 
 // of +1.6 % with the cheap formula.
 struct OdeGrid {
     // geometric steps h0 q^k, k < NSTEP, that sum to the phase length
-    static constexpr int NSTEP = 24;
+    static constexpr int NSTEP = 16;
     double h0 = 0.0, q = 1.0;
     explicit OdeGrid(double dur) {
         if (!(dur > 0.0)) return;
@@ -230,9 +230,9 @@ struct PairOde {
             const double F2 = bn - b - h * (k1 * an + k2 * (1.0 - an) - 2.0 * k2 * bn - pab);
             const double J11 = 1.0 + h * (k1 + k2 + p * bn), J12 = h * p * an;
             const double J21 = -h * (k1 - k2 - p * bn), J22 = 1.0 + h * (2.0 * k2 + p * an);
-            const double det = J11 * J22 - J12 * J21;
-            an = std::min(1.0, std::max(0.0, an - (F1 * J22 - F2 * J12) / det));
-            bn = std::min(1.0, std::max(0.0, bn - (J11 * F2 - J21 * F1) / det));
+            const double inv = 1.0 / (J11 * J22 - J12 * J21);
+            an = std::min(1.0, std::max(0.0, an - (F1 * J22 - F2 * J12) * inv));
+            bn = std::min(1.0, std::max(0.0, bn - (J11 * F2 - J21 * F1) * inv));
         }
         *ao = an; *bo = bn;
     }
@@ -865,6 +865,8 @@ double replicate_estimate(const PointDev &p, int DIM, const SprSim *sim, const S
 
 // the last deal is kept: a build asks for it once per call (twice through sprb200_deal_indices), and a caller that
 // repeats a build asks for the same one again
+constexpr int64_t DEAL_ODE_MAX_POINTS = 400000;
+
 struct DealMemo {
     std::mutex mu;
     std::vector<unsigned char> key;
@@ -903,8 +905,18 @@ int deal_points(const SprGrid *grid, const SprSim *sim, const SprRun *run, int n
         *out = g_deal_memo.deal;
         return SPRB200_OK;
     }
+    // The kinetic estimate costs 3 us per point; the cheap formula's errors average out once a rank gets enough points
+    // (paper-scale grid, 189,000 points per rank: slowest rank +0.5 % with it; 10,000 per rank: +1.6 %).
     std::vector<double> cost((size_t)P);
-    deal_costs(P, sim, [&](int64_t i) { PointDev p; grid_point(grid, i, &p); return p; }, cost.data());
+    if (P <= DEAL_ODE_MAX_POINTS) {
+        deal_costs(P, sim, [&](int64_t i) { PointDev p; grid_point(grid, i, &p); return p; }, cost.data());
+    } else {
+        for (int64_t i = 0; i < P; ++i) {
+            PointDev p;
+            grid_point(grid, i, &p);
+            cost[(size_t)i] = cost_estimate(p, sim->N, sim->DIM, sim->L, sim->tstop, sim->tstop_AtoB);
+        }
+    }
     std::vector<std::pair<double, int64_t>> keyed((size_t)P);
     for (int64_t i = 0; i < P; ++i) {
         PointDev p;
