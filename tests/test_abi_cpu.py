@@ -164,3 +164,64 @@ def test_dist_entry_points_fail_loudly_without_gpu(built_lib):
     with pytest.raises(_lib.SprB200Error) as e:
         _lib.build_table_multi([0], grid, sim, _lib.make_run(nsims=2))
     assert e.value.code == _lib.ERR_NO_DEVICE
+
+
+def test_kinetic_cost_estimate_tracks_executed_events(built_lib, oracle_libs):
+    """sprb200_estimate_cost = (expected SSA events + save slots) x (1 + degree/32), the events from the mean-field
+    kinetics of the four channels (forward_simulator.jl:132-135 rates).  Ground truth without a GPU: the mirror
+    executes the kernels' event sequence bit for bit, so its event count IS the GPU's."""
+    import sprb200
+    from sprb200 import _lib
+    from oracle import mirror_oracle as M
+    L = _lib.domain_length()
+    tsave = np.linspace(0, 600, 601)
+    sim = sprb200.SimSpec(1000, 3, L, 600.0, 150.0, tsave)
+    grid = _lib.make_grid((-3, 2), (-4, -1), (-3, 1.5), (2, 35), (10, 10, 10, 10))
+    pts = _lib.grid_points(grid)
+    rng = np.random.default_rng(5)
+    sel = rng.choice(len(pts), 48, replace=False)
+    cost = _lib.estimate_cost(sim, pts[sel])
+    deg = np.minimum(999.0, 999.0 * 4.0 / 3.0 * np.pi * pts[sel, 3] ** 3 / L ** 3)
+    est = cost / (1.0 + deg / 32.0) - 600.0
+    msim = M.Sim(N=1000, DIM=3, tstop=600.0, tstop_AtoB=150.0, tsave=tsave)
+    true = np.array([np.mean([M.trajectory(msim, *pts[k], 99, int(k), r)[2] for r in range(2)]) for k in sel])
+    big = true > 2000
+    assert big.sum() >= 20
+    ratio = true[big] / est[big]
+    assert 0.93 < true.sum() / est.sum() < 1.07, (true.sum(), est.sum())
+    assert ratio.min() > 0.6 and ratio.max() < 1.5, (ratio.min(), ratio.max())
+
+
+def test_cost_estimate_and_deal_edge_cases(built_lib):
+    """finite positive costs at the corners of the parameter space; the deal is a partition on both of its paths
+    (kinetic costs up to 400,000 points, the closed formula above), deterministic, and memoised"""
+    import math
+    import time
+    import sprb200
+    from sprb200 import _lib
+    L = _lib.domain_length()
+    pts = np.array([[0, 0, 0, 0], [1e-3, 0, 0, 10], [0, 1e-2, 5, 35], [1e2, 1e-1, 31.6, 35], [1e-5, 1e-4, 1e-3, 2],
+                    [1e2, 1, 1e3, 500], [1e6, 1e6, 1e6, 35], [1e-300, 1e-300, 1e-300, 1e-3]], dtype=float)
+    for N, DIM, tstop, toff in ((1000, 3, 600.0, 150.0), (1000, 3, 600.0, math.inf), (1000, 3, 600.0, -5.0), (1, 3, 600.0, 150.0),
+                                (2, 2, 10.0, 3.0), (1000, 2, 600.0, 0.0), (1000, 3, 1e-6, 1e-7)):
+        c = _lib.estimate_cost(sprb200.SimSpec(N, DIM, L, tstop, toff, np.linspace(0, tstop, 11)), pts)
+        assert np.all(np.isfinite(c)) and np.all(c >= 600.0), (N, DIM, tstop, toff, c)
+    sim = sprb200.SimSpec(1000, 3, L, 600.0, 150.0, np.linspace(0, 600, 601))
+    # more expensive where more happens: faster rates, wider reach
+    lo, hi = _lib.estimate_cost(sim, np.array([[1e-2, 1e-3, 1e-2, 10.0], [1e0, 1e-1, 1e1, 30.0]]))
+    assert hi > 20 * lo
+    run = _lib.make_run(variance=(0.01, 15, 250))
+    for size, world in (((9, 8, 7, 6), 3), ((21, 20, 31, 31), 8)):      # 3,024 and 403,620 points
+        grid = _lib.make_grid((-5, 2), (-4, 0), (-3, 1.5), (2, 35), size)
+        P = int(np.prod(size))
+        t0 = time.time()
+        first = [_lib.deal_indices(grid, sim, world, r, run) for r in range(world)]
+        t1 = time.time()
+        again = [_lib.deal_indices(grid, sim, world, r, run) for r in range(world)]
+        t2 = time.time()
+        assert np.array_equal(np.sort(np.concatenate(first)), np.arange(1, P + 1))
+        assert max(len(d) for d in first) - min(len(d) for d in first) <= 1
+        assert all(np.array_equal(a, b) for a, b in zip(first, again))
+        assert t2 - t1 <= (t1 - t0) + 0.5                                  # served from the memo
+    one = _lib.deal_indices(_lib.make_grid((-5, 2), (-4, 0), (-3, 1.5), (2, 35), (9, 8, 7, 6)), sim, 1, 0)
+    assert np.array_equal(one, np.arange(1, 3025))
