@@ -160,8 +160,8 @@ class H5Writer:
         return struct.pack("<BBB5x", 1, len(shape), 0) + b"".join(struct.pack("<Q", d) for d in shape)
 
     def _dtype_message(self, t):
-        if t.committed_addr is not None:           # shared message, version 2, type 0 = committed datatype
-            return self._message(0x03, struct.pack("<BBQ", 2, 0, t.committed_addr), flags=0x02)
+        if t.committed_addr is not None:           # shared message as libhdf5 encodes it: version 2, type 2 = committed
+            return self._message(0x03, struct.pack("<BBQ", 2, 2, t.committed_addr), flags=0x02)
         return self._message(0x03, t.body)
 
     def _attribute(self, name, value):

@@ -133,7 +133,7 @@ def fsck(path):
             dims = struct.unpack_from("<%dQ" % rank, space, 8)
             assert space[0] == 1 and space[2] == 0
             if tflags & 2:
-                assert tbody[0] == 2
+                assert tbody[0] == 2 and tbody[1] == 2        # H5O_SHARED_VERSION_2, H5O_SHARE_TYPE_COMMITTED
                 taddr, = struct.unpack_from("<Q", tbody, 2)
                 assert seen.get(taddr) == "type"            # committed before it is used
                 size = seen[("size", taddr)]
