@@ -170,3 +170,23 @@ def test_monovalent_fit_recovers_manufactured_parameters(built_lib):
         sol = api.monovalent_fit_spr_data(ad, toff, u0, lb, ub)
         assert np.max(np.abs(10.0 ** sol.u - np.array([kon, koff, CP]))) < 1e-10
         assert sol.minimum < 1e-18
+
+
+def test_get_aligned_data_reference_known_answer(built_lib, tmp_path):
+    """the reference's own test (test/aligned_data.jl:6-15): a two-curve file with a ragged second curve and trailing
+    empty rows; expected times, data, antigen concentration (from the file name) and antibody concentrations (header)"""
+    from sprb200 import api
+    times = [[5.0, 6.0, 7.0, 8.0, 9.0, 10.0, 11.0], [5.0, 6.0, 7.0, 8.0]]
+    refdata = [[.821, 1.12, 1.22, 1.52, 1.42, 1.82, 1.92], [3.80, 4.30, 4.80, 5.50]]
+    fn = tmp_path / "tester-13.8_aligned.csv"
+    with open(fn, "w") as f:
+        f.write("time (s),25,time (s),100\n")
+        for k in range(7):
+            second = "%.2E,%.2E" % (times[1][k], refdata[1][k]) if k < 4 else ","
+            f.write("%.2E,%.2E,%s\n" % (times[0][k], refdata[0][k], second))
+        f.write(",,,\n" * 5)
+    ad = api.get_aligned_data(str(fn))
+    assert [list(t) for t in ad.times] == times
+    assert [list(d) for d in ad.refdata] == refdata
+    assert ad.antigenconcen == 13.8
+    assert list(ad.antibodyconcens) == [25.0, 100.0]
