@@ -1,9 +1,12 @@
 """CPU: host-side mirror of the reference interface (sprb200/api.py) -- the parts that need no GPU.
 Reads like the reference's test/callbacks.jl."""
 import math
+import os
 
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_total_bound_outputter_mean_and_sem(built_lib):
@@ -131,3 +134,41 @@ def test_raw_surrogate_handover_round_trips(built_lib, tmp_path):
               "antibodyconcen", "CP", "N", "tstop", "tstop_AtoB", "tsave", "L", "DIM"):
         assert np.array_equal(np.asarray(back[k], dtype=np.float64), np.asarray(meta[k], dtype=np.float64)), k
     assert math.isinf(float(back["tstop_AtoB"]))
+
+
+def test_slice_workflow_example_cli(built_lib, tmp_path):
+    """examples/make_surrogate_slices.py (the reference's cluster_scripts workflow): metadata -> one slice file per
+    job -> merge, on the CPU with fabricated slice columns (the simulation itself is covered on the GPU): the job
+    ranges tile 1..P like queue_job.sh:7-17 and the merged FirstMoment holds column idx at CartesianIndices[idx]."""
+    import importlib.util
+    from sprb200 import api
+    spec = importlib.util.spec_from_file_location("make_surrogate_slices", os.path.join(ROOT, "examples", "make_surrogate_slices.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    d = str(tmp_path / "sur")
+    size = (3, 2, 2, 2)
+    cli.main(["metadata", d] + [str(n) for n in size] + ["--seed", "7"])
+    meta = api.load(os.path.join(d, "surrogate_metadata.jld"))
+    assert tuple(int(v) for v in meta["surrogate_size"]) == size + (601,) and int(meta["seed"]) == 7
+    assert tuple(meta["logkon_range"]) == (-5.0, 2.0) and float(meta["tstop_AtoB"]) == 150.0
+    P, T, njobs = 24, 601, 5
+    covered = []
+    for i in range(1, njobs + 1):
+        lo, hi = cli.job_range(P, i, njobs)
+        covered += list(range(lo, hi + 1))
+        cols = np.asfortranarray(np.arange(lo, hi + 1)[None, :] + 1e-3 * np.arange(T)[:, None])     # [T, nidx]
+        api._save(os.path.join(d, "surrogate_slice_%d.jld" % i), dict(surrogate_slice=cols, idxstart=np.int64(lo), idxend=np.int64(hi)))
+    assert covered == list(range(1, P + 1))
+    cli.main(["merge", d, str(njobs)])
+    with pytest.raises(FileExistsError):
+        cli.main(["merge", d, str(njobs)])
+    cli.main(["merge", d, str(njobs), "--force"])
+    sur = api.Surrogate(os.path.join(d, "surrogate_slice_merged.jld"))
+    assert sur.table.shape == size + (T,)
+    lin = 1
+    for i4 in range(size[3]):
+        for i3 in range(size[2]):
+            for i2 in range(size[1]):
+                for i1 in range(size[0]):                       # kon fastest (surrogate.jl:284)
+                    assert np.array_equal(sur.table[i1, i2, i3, i4], lin + 1e-3 * np.arange(T))
+                    lin += 1
