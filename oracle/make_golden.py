@@ -41,9 +41,10 @@ def cells(xml):
     return out
 
 
-def main():
-    raw = open(SRC, "rb").read()
-    z = zipfile.ZipFile(SRC)
+def extract(src):
+    """the savefit workbook at `src` (the reference's recorded one, or one written by api.savefit) as a dict"""
+    raw = open(src, "rb").read()
+    z = zipfile.ZipFile(src)
     shared = re.findall(r"<si><t[^>]*>(.*?)</t></si>", z.read("xl/sharedStrings.xml").decode(), re.S)
     s1 = cells(z.read("xl/worksheets/sheet1.xml").decode())
     s2 = cells(z.read("xl/worksheets/sheet2.xml").decode())
@@ -90,13 +91,19 @@ def main():
         "data": [cols["B"], cols["E"]],
         "sim_mean": [cols["C"], cols["F"]],
     }
+    return gold
+
+
+def main():
+    gold = extract(SRC)
     with open(OUT, "w") as f:
         json.dump(gold, f, indent=0)
-    print("wrote", os.path.normpath(OUT), "rows", len(cols["A"]), "params", internal, physical, fitness)
+    internal = gold["internal_params"]
+    print("wrote", os.path.normpath(OUT), "rows", len(gold["times"]), "params", internal, gold["physical_params"], gold["fitness"])
     # sanity: value*nsims*N/CP should be an integer count
     CP = 10.0 ** internal["logCP"]
-    x = cols["C"][140] / CP * 250 * 1000
-    print("row 142 count check:", cols["A"][140], cols["C"][140], x)
+    x = gold["sim_mean"][0][140] / CP * 250 * 1000
+    print("row 142 count check:", gold["times"][140], gold["sim_mean"][0][140], x)
 
 
 if __name__ == "__main__":

@@ -19,7 +19,10 @@ Same names, argument meaning and error behaviour as the Julia package (paths und
   surrogate_sprdata_error, checkranges,
   rescale_logkon_max, fit_spr_data,
   optpars_to_physpars,
-  update_pars_and_run_spr_sim, fitted_curves   src/fitting.jl:36-241, 264-278
+  update_pars_and_run_spr_sim, fitted_curves,
+  savefit                                      src/fitting.jl:36-241, 264-278, 320-431
+  monovalent_total_bound, monovalent_sprdata_error,
+  monovalent_fit_spr_data                      src/monovalent_fitting.jl:22-71
 
 Everything that simulates runs on the GPU through libsprb200.so; there is no CPU path here.
 Files: a file name ending in `.jld` is written and read in the reference's own JLD (HDF5) layout by
@@ -822,6 +825,104 @@ def fitted_curves(optsol, aligneddat, simpars, seed=None, device=0):
     for i, t in enumerate(times):
         out.append(cps[i] * res["mean"][i][np.searchsorted(tall, t)])
     return out
+
+
+# ------------------------------------------------------------------ savefit (fitting.jl:320-431)
+def _xlsx_write(fname, sheets):
+    """minimal SpreadsheetML workbook (no spreadsheet package in this image): `sheets` = [(name, {(row, col): value})],
+    1-based rows and columns, values float / int / str; strings go through the shared-string table like Excel's own"""
+    import zipfile
+    from xml.sax.saxutils import escape
+    shared, sidx = [], {}
+
+    def colname(c):
+        out = ""
+        while c:
+            c, r = divmod(c - 1, 26)
+            out = chr(65 + r) + out
+        return out
+
+    def cell(r, c, v):
+        ref = "%s%d" % (colname(c), r)
+        if isinstance(v, str):
+            if v not in sidx:
+                sidx[v] = len(shared)
+                shared.append(v)
+            return '<c r="%s" t="s"><v>%d</v></c>' % (ref, sidx[v])
+        return '<c r="%s"><v>%s</v></c>' % (ref, repr(float(v)) if not isinstance(v, (int, np.integer)) else str(int(v)))
+
+    ns = 'xmlns="http://schemas.openxmlformats.org/spreadsheetml/2006/main"'
+    rel = "http://schemas.openxmlformats.org/officeDocument/2006/relationships"
+    head = '<?xml version="1.0" encoding="UTF-8" standalone="yes"?>\n'
+    xml_sheets = []
+    for _, cells in sheets:
+        rows = {}
+        for (r, c), v in cells.items():
+            rows.setdefault(r, []).append((c, v))
+        body = "".join('<row r="%d">%s</row>' % (r, "".join(cell(r, c, v) for c, v in sorted(rows[r]))) for r in sorted(rows))
+        xml_sheets.append(head + '<worksheet %s><sheetData>%s</sheetData></worksheet>' % (ns, body))
+    n = len(sheets)
+    with zipfile.ZipFile(fname, "w", zipfile.ZIP_DEFLATED) as z:
+        z.writestr("[Content_Types].xml", head + '<Types xmlns="http://schemas.openxmlformats.org/package/2006/content-types">'
+                   '<Default Extension="rels" ContentType="application/vnd.openxmlformats-package.relationships+xml"/>'
+                   '<Default Extension="xml" ContentType="application/xml"/>'
+                   '<Override PartName="/xl/workbook.xml" ContentType="application/vnd.openxmlformats-officedocument.spreadsheetml.sheet.main+xml"/>'
+                   + "".join('<Override PartName="/xl/worksheets/sheet%d.xml" ContentType="application/vnd.openxmlformats-officedocument.spreadsheetml.worksheet+xml"/>' % (i + 1) for i in range(n))
+                   + '<Override PartName="/xl/sharedStrings.xml" ContentType="application/vnd.openxmlformats-officedocument.spreadsheetml.sharedStrings+xml"/></Types>')
+        z.writestr("_rels/.rels", head + '<Relationships xmlns="http://schemas.openxmlformats.org/package/2006/relationships">'
+                   '<Relationship Id="rId1" Type="%s/officeDocument" Target="xl/workbook.xml"/></Relationships>' % rel)
+        z.writestr("xl/workbook.xml", head + '<workbook %s xmlns:r="%s"><sheets>%s</sheets></workbook>' % (
+            ns, rel, "".join('<sheet name="%s" sheetId="%d" r:id="rId%d"/>' % (escape(nm), i + 1, i + 1) for i, (nm, _) in enumerate(sheets))))
+        z.writestr("xl/_rels/workbook.xml.rels", head + '<Relationships xmlns="http://schemas.openxmlformats.org/package/2006/relationships">'
+                   + "".join('<Relationship Id="rId%d" Type="%s/worksheet" Target="worksheets/sheet%d.xml"/>' % (i + 1, rel, i + 1) for i in range(n))
+                   + '<Relationship Id="rId%d" Type="%s/sharedStrings" Target="sharedStrings.xml"/></Relationships>' % (n + 1, rel))
+        for i, x in enumerate(xml_sheets):
+            z.writestr("xl/worksheets/sheet%d.xml" % (i + 1), x)
+        z.writestr("xl/sharedStrings.xml", head + '<sst %s count="%d" uniqueCount="%d">%s</sst>' % (
+            ns, len(shared), len(shared), "".join("<si><t>%s</t></si>" % escape(t) for t in shared)))
+
+
+def savefit(optsol, aligneddat, surrogate, simpars, outfile, monofit=None, seed=None, device=0, curves=None):
+    """fitting.jl:320-431: `<outfile>_fit.xlsx` with the reference's two sheets -- "SPR and Fit Curves" (per antibody
+    concentration: times, "Experimental Data <c> nM", "Bivalent Fit <c> nM" = mean of simpars.nsims forward simulations
+    at the fitted parameters, optionally "Monovalent Fit <c> nM") and "Fit Parameters" (internal and physical best-fit
+    parameters, fitnesses, the monovalent parameters).  `curves` = the simulated columns if they already exist
+    (fitted_curves is called otherwise: one batched GPU call)."""
+    times, refdata, abcs = aligneddat.times, aligneddat.refdata, list(aligneddat.antibodyconcens)
+    params = [float(v) for v in (optsol.u if hasattr(optsol, "u") else optsol)]
+    if curves is None:
+        curves = fitted_curves(optsol, aligneddat, simpars, seed=seed, device=device)
+    toff = simpars.tstop_AtoB
+    cpt = 3 if monofit is None else 4
+    s1 = {}
+    for j, abc in enumerate(abcs):
+        c0 = cpt * j + 1
+        cols = [("times", times[j]), ("Experimental Data %s nM" % abc, refdata[j]), ("Bivalent Fit %s nM" % abc, curves[j])]
+        if monofit is not None:
+            cols.append(("Monovalent Fit %s nM" % abc,
+                         monovalent_total_bound(tuple(10.0 ** np.asarray(monofit.u, dtype=np.float64)), (abc, toff), times[j])))
+        for k, (h, col) in enumerate(cols):
+            s1[(1, c0 + k)] = h
+            for r, v in enumerate(np.asarray(col, dtype=np.float64)):
+                s1[(r + 2, c0 + k)] = float(v)
+    simagc = inv_cubic_nm_to_muM(getantigenconcen(simpars))
+    if not math.isclose(simagc, surrogate.surpars.antigenconcen, rel_tol=0.0, abs_tol=1e-12):   # fitting.jl:393-394
+        raise AssertionError("simulation antigen concentration %r differs from the surrogate's %r" % (simagc, surrogate.surpars.antigenconcen))
+    phys = optpars_to_physpars(params, aligneddat, surrogate)
+    s2 = {(1, 1): "Best fit parameters (internal):", (1, 4): "Best fit parameters (physical):"}
+    for r, (a, b, va, vb) in enumerate(zip(("logkon", "logkoff", "logkonb", "reach", "logCP"),
+                                           ("kon", "koff", "konb", "reach", "CP"), params, phys)):
+        s2[(r + 2, 1)], s2[(r + 2, 2)], s2[(r + 2, 4)], s2[(r + 2, 5)] = a, va, b, float(vb)
+    s2[(8, 1)], s2[(8, 2)] = "Bivalent Fitness", float(getattr(optsol, "minimum", math.nan))
+    if monofit is not None:
+        s2[(9, 1)], s2[(9, 2)] = "Monovalent Fitness", float(monofit.minimum)
+        s2[(11, 1)], s2[(11, 2)] = "Monofit return code:", str(getattr(monofit, "retcode", "Success"))
+        s2[(1, 7)] = "Monovalent fit parameters (physical):"
+        for r, (nm, v) in enumerate(zip(("kon", "koff", "CP"), 10.0 ** np.asarray(monofit.u, dtype=np.float64))):
+            s2[(r + 2, 7)], s2[(r + 2, 8)] = nm, float(v)
+    fname = outfile + "_fit.xlsx"
+    _xlsx_write(fname, [("SPR and Fit Curves", s1), ("Fit Parameters", s2)])
+    return fname
 
 
 # ------------------------------------------------------------------ monovalent model (closed form, host only)

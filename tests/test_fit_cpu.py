@@ -190,3 +190,34 @@ def test_get_aligned_data_reference_known_answer(built_lib, tmp_path):
     assert [list(d) for d in ad.refdata] == refdata
     assert ad.antigenconcen == 13.8
     assert list(ad.antibodyconcens) == [25.0, 100.0]
+
+
+def test_savefit_workbook_is_read_by_the_golden_extractor(built_lib, tmp_path):
+    """fitting.jl:320-431: api.savefit writes the reference's two-sheet workbook; the extractor that reads the
+    reference's own recorded workbook into tests/golden/ (oracle/make_golden.py) reads it back identically"""
+    from oracle import make_golden
+    from sprb200 import api
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "fit_curves_golden.json")))
+    t = np.array(gold["times"])
+    ad = api.AlignedData([t, t], gold["data"], gold["antibody_nM"], 13.8)
+    ip = gold["internal_params"]
+    sol = api.OptSolution(np.array([ip["logkon"], ip["logkoff"], ip["logkonb"], ip["reach"], ip["logCP"]]), gold["fitness"], 0, 0)
+    surpars = api.SurrogateParams((-5.0, 2.0), (-4.0, 0.0), (-3.0, 1.5), (2.0, 35.0))
+    simpars = api.SimParams(tstop=600.0, tstop_AtoB=150.0, tsave=t)
+    sur = api.Surrogate(np.zeros((2, 2, 2, 2, 2)), surpars=surpars, simpars=simpars)
+    fn = api.savefit(sol, ad, sur, simpars, str(tmp_path / "parameters.xlsx"), curves=gold["sim_mean"])
+    assert fn.endswith("parameters.xlsx_fit.xlsx")
+    back = make_golden.extract(fn)
+    for k in ("antibody_nM", "internal_params", "fitness", "times", "data", "sim_mean"):
+        assert back[k] == gold[k], k
+    for k, v in gold["physical_params"].items():                  # the reference's own conversion, to rounding
+        assert math.isclose(back["physical_params"][k], v, rel_tol=1e-12), k
+    # with a monovalent fit: four columns per concentration and the extra parameter block
+    mono = api.OptSolution(np.log10([1e-4, 0.05, 100.0]), 123.0, 1, 1)
+    fn2 = api.savefit(sol, ad, sur, simpars, str(tmp_path / "with_mono"), monofit=mono, curves=gold["sim_mean"])
+    import zipfile
+    z = zipfile.ZipFile(fn2)
+    shared = z.read("xl/sharedStrings.xml").decode()
+    assert "Monovalent Fit 25.0 nM" in shared and "Monovalent fit parameters (physical):" in shared and "Monofit return code:" in shared
+    assert 'r="H587"' in z.read("xl/worksheets/sheet1.xml").decode()
+    assert "SPR and Fit Curves" in z.read("xl/workbook.xml").decode() and "Fit Parameters" in z.read("xl/workbook.xml").decode()
