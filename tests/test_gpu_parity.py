@@ -25,7 +25,11 @@ replicates and >= 10^4 (C1) / 2x10^3 (stress cases) oracle replicates per pair, 
   D. the north-star rule itself in a seed-free form: a real bias pushes EVERY pair beyond 3 SE, chance pushes one
      pair in six, so at least one of the K pairs must lie within 3 SE at every bin (null P(all 4 exceed) =
      0.1 %), and no pair may exceed 5 SE anywhere (Bonferroni 0.03 % per pair);
-  E. events per trajectory agree within 0.5 % (same process => same event count; SE ~ 0.05 %).
+  E. events per trajectory agree within 0.5 % (same process => same event count; SE ~ 0.05 %);
+  F. second moments: the replicate-to-replicate variance summed over the bins and pairs, GPU / oracle, within 10 % of 1
+     (what `vars`/`sems` of the outputter and the VarianceTerminator's stopping index are made of; the null scatter of
+     this ratio is 0.7 % with 10^4 and 2 % with 2x10^3 oracle replicates per pair -- tests/tools/parity_replay_cpu.py
+     replays this test on the CPU with the bit-identical mirror).
 """
 import json
 import os
@@ -82,7 +86,10 @@ def parity_statistics(pairs):
     num = np.zeros_like(pairs[0][0])
     den = np.zeros_like(pairs[0][0])
     zs, maxabs = [], []
+    gvsum = rvsum = 0.0
     for gm, gv, gn, rm, rv, rn in pairs:
+        gvsum += float(np.sum(gv))
+        rvsum += float(np.sum(rv))
         se2 = gv / gn + rv / rn
         ok = se2 > 0
         assert np.all(gm[~ok] == rm[~ok])          # deterministic bins (t = 0) must agree exactly
@@ -96,7 +103,8 @@ def parity_statistics(pairs):
     allz = np.concatenate(zs)
     return dict(pool_max=float(np.abs(zpool).max()), mean_z=float(allz.mean()), mean_z2=float((allz ** 2).mean()),
                 pair_max=maxabs, n_within_3=int(sum(m < 3.0 for m in maxabs)),
-                frac_bins_beyond_3=float((np.abs(allz) > 3.0).mean()))
+                frac_bins_beyond_3=float((np.abs(allz) > 3.0).mean()),
+                var_ratio=gvsum / rvsum if rvsum > 0 else 1.0)
 
 
 def assert_parity(st, K, label):
@@ -104,6 +112,7 @@ def assert_parity(st, K, label):
     assert abs(st["mean_z"]) < 4.0 / np.sqrt(K), (label, st)        # B
     assert st["mean_z2"] < 3.5, (label, st)                         # C
     assert st["n_within_3"] >= 1 and max(st["pair_max"]) < 5.0, (label, st)   # D
+    assert abs(st["var_ratio"] - 1.0) < 0.10, (label, st)           # F
 
 
 @pytest.fixture(scope="module")
