@@ -23,7 +23,9 @@ Secondary blocks in the same JSON line: `strong` (a FIXED-size job -- a 14x10x10
 paper-scale C3 ranges with the reference's VarianceTerminator(0.01,15,250) -- split over the N ranks, with
 the sha256 of the gathered table: identical for every N), `c3_sample` (that job projected to the full
 1,512,000-point grid, next to the CPU port timed on a stratified sample of the same lattice, N=1 only),
-`small_batch` (BASELINE configs 0 and 3 with the reference's nsims = 1000).
+`small_batch` (BASELINE configs 0 and 3 with the reference's nsims = 1000), `parity` (sha256 of the host table of one
+C2 build, outside the timed regions, next to the sha256 the sequential CPU mirror oracle/spr_mirror.c gives for the same
+grid and seed -- tests/golden/bench_c2_table_sha256.json, written by tests/tools/bench_tables_cpu.py).
 Timing: CUDA events, barrier + synchronize on both sides, max over ranks.  One JSON line on stdout from rank 0.
 
 --impl reference: the reference's own CPU implementation of the path (oracle/spr_ref.c: the reference is Julia
@@ -51,6 +53,7 @@ NREP = 100
 TSTOP, TOFF, NT = 600.0, 150.0, 601
 NPART, DIM = 1000, 3
 SEED = 20231
+E2E_WARM_SEED_OFFSET = 50      # seed of the untimed end-to-end warm-up step, whose host table is hashed (parity block)
 METRIC = "ssa_events_per_sec"
 UNIT = "events/s"
 ISSUE_PER_CLK = 148 * 4          # warp-instructions per clock, chip-wide
@@ -378,12 +381,31 @@ def main():
     traj_total = P * NREP * K
 
     # ---- end to end through the host-buffer call (H2D inputs + D2H of the table inside the region), all K steps
+    last = {}
+
     def e2e_step(seed):
         run = _lib.make_run(nsims=NREP, seed=seed)
         tab, nu, nev = eng.build_table_dist(grid, sim, run, host=(rank == 0), want_counts=(rank == 0))
+        last["table"] = tab
         return eng.stats()["events"]
 
-    e2e_step(SEED + 50)
+    e2e_step(SEED + E2E_WARM_SEED_OFFSET)
+    # bit-exact parity at full size, outside every timed region: the host table of this warm-up step against the
+    # sha256 the sequential CPU mirror gives for the same grid and seed (tests/tools/bench_tables_cpu.py)
+    parity = None
+    if rank == 0:
+        try:
+            parity = {"table_sha256": hashlib.sha256(np.ascontiguousarray(last["table"]).tobytes()).hexdigest(),
+                      "seed": SEED + E2E_WARM_SEED_OFFSET, "cpu_mirror_sha256": None, "match": None,
+                      "what": "host table [T][P] of one C2 build through sprb200_build_table_dist vs the same table built "
+                              "by oracle/spr_mirror.c on the CPU (tests/golden/bench_c2_table_sha256.json)"}
+            with open(os.path.join(ROOT, "tests", "golden", "bench_c2_table_sha256.json")) as f:
+                gold = json.load(f)
+            if gold.get("seed") == parity["seed"] and gold.get("replicates") == NREP and str(world) in gold:
+                parity["cpu_mirror_sha256"] = gold[str(world)]["table_sha256"]
+                parity["match"] = parity["cpu_mirror_sha256"] == parity["table_sha256"]
+        except Exception as e:                       # never let the check cost the bench line
+            parity = {"error": repr(e)} if parity is None else dict(parity, error=repr(e))
     barrier()
     t0 = time.perf_counter()
     ev_e2e = 0
@@ -498,6 +520,8 @@ def main():
                     "steps": K},
             "roofline": roofline, "roofline_issue": roofline_issue,
         }
+        if parity is not None:
+            out["parity"] = parity
         if strong is not None:
             out["strong"] = strong
             out["small_batch"] = small

@@ -225,3 +225,19 @@ def test_cost_estimate_and_deal_edge_cases(built_lib):
         assert t2 - t1 <= (t1 - t0) + 0.5                                  # served from the memo
     one = _lib.deal_indices(_lib.make_grid((-5, 2), (-4, 0), (-3, 1.5), (2, 35), (9, 8, 7, 6)), sim, 1, 0)
     assert np.array_equal(one, np.arange(1, 3025))
+
+
+def test_bench_parity_fixture_matches_the_bench_workload():
+    """bench.py compares the hash of its C2 host table with tests/golden/bench_c2_table_sha256.json (built on the CPU
+    by oracle/spr_mirror.c, tests/tools/bench_tables_cpu.py): the fixture must describe the workload bench.py runs"""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    B = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(B)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_c2_table_sha256.json")))
+    assert gold["seed"] == B.SEED + B.E2E_WARM_SEED_OFFSET and gold["replicates"] == B.NREP
+    assert gold["1"]["points"] == B.NK[0] * B.NK[1] * B.NK[2] * B.NREACH_PER_GPU
+    for k, v in gold.items():
+        if k.isdigit():
+            assert v["points"] == gold["1"]["points"] * int(k) and len(v["table_sha256"]) == 64
