@@ -108,3 +108,25 @@ def test_mirror_variance_rule_matches_reference_rule(oracle_libs):
             break
     assert o["n_used"] == n_ref
     assert 5 < n_ref < 80
+
+
+def test_surrogate_file_built_on_a_b200_equals_the_mirror(oracle_libs, built_lib):
+    """tests/golden/b200_built_surrogate_2x2x2x2.jld was written on a B200 by `examples/make_surrogate.py t.jld --nsims 20`
+    (profiles/r2_examples_on_gpu.txt: ranges of make_surrogate.jl, 2x2x2x2 points x 20 FIXED replicates, seed 20231, through
+    api.save_surrogate -> sprb200_build_table -> sprb200/jld.py).  The sequential mirror rebuilds every column bit for bit:
+    RNG keys (seed, linear index - 1, replicate), integer sums, one division per element, FirstMoment layout."""
+    import os
+    from sprb200 import _lib, jld
+    d = jld.load(os.path.join(os.path.dirname(__file__), "golden", "b200_built_surrogate_2x2x2x2.jld"))
+    tab = np.asarray(d["FirstMoment"])
+    assert tab.shape == (2, 2, 2, 2, 601) and tuple(d["surrogate_size"]) == (2, 2, 2, 2, 601)
+    assert tuple(d["logkon_range"]) == (-3.0, 2.0) and tuple(d["reach_range"]) == (2.0, 35.0) and int(d["N"]) == 1000
+    tsave = np.asarray(d["tsave"])
+    grid = _lib.make_grid(d["logkon_range"], d["logkoff_range"], d["logkonb_range"], d["reach_range"], (2, 2, 2, 2))
+    pts = _lib.grid_points(grid)
+    gpu = tab.reshape(-1, 601, order="F")                                # [P][T], kon fastest (surrogate.jl:284)
+    for k in range(16):
+        sm = M.Sim(N=1000, DIM=3, L=float(d["L"]), tstop=float(d["tstop"]), tstop_AtoB=float(d["tstop_AtoB"]), tsave=tsave)
+        o = M.point(sm, *pts[k], 20231, k, nsims=20)
+        assert o["n_used"] == 20
+        assert np.array_equal(gpu[k], o["sum"].astype(np.float64) / (20.0 * 1000.0)), k
