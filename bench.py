@@ -25,7 +25,10 @@ the sha256 of the gathered table: identical for every N), `c3_sample` (that job 
 1,512,000-point grid, next to the CPU port timed on a stratified sample of the same lattice, N=1 only),
 `small_batch` (BASELINE configs 0 and 3 with the reference's nsims = 1000), `parity` (sha256 of the host table of one
 C2 build, outside the timed regions, next to the sha256 the sequential CPU mirror oracle/spr_mirror.c gives for the same
-grid and seed -- tests/golden/bench_c2_table_sha256.json, written by tests/tools/bench_tables_cpu.py).
+grid and seed -- tests/golden/bench_c2_table_sha256.json, written by tests/tools/bench_tables_cpu.py).  `strong` and
+every `small_batch` case carry a `parity` entry of the same kind (table and stopping-index hashes of the strong job;
+integer sums and event count of the small-batch warm call) against tests/golden/bench_strong_table_sha256.json and
+bench_small_batch_sha256.json (tests/tools/strong_table_cpu.py, bench_small_cpu.py); `match` null = no fixture.
 Timing: CUDA events, barrier + synchronize on both sides, max over ranks.  One JSON line on stdout from rank 0.
 
 --impl reference: the reference's own CPU implementation of the path (oracle/spr_ref.c: the reference is Julia
@@ -66,6 +69,41 @@ C3_SIZE = (42, 40, 30, 30)
 C3_LATTICE = (14, 10, 10, 10)
 C3_TERM = (0.01, 15, 250)
 L_DEFAULT = (NPART / (6.02214076e-7 * (500 / 149 / 26795 * 1000000))) ** (1.0 / 3.0)   # parameters.jl:4,138-139
+SMALL_NSIMS, SMALL_TOFF = 1000, 150.0      # small-batch block: the reference's nsims (parameters.jl:124-135)
+
+
+def small_batch_cases(L):
+    """name -> ([kon_eff, koff, konb, reach], box length, tstop): BASELINE configs 0 (the documented fit at 25 nM,
+    reach 30) and 3b (reach 50 at twice the default antigen density)"""
+    return {"C1_default_reach30_25nM_nsims1000": ([10 ** -2.8789331867029184, 10 ** -1.3886105070021626,
+                                                   10 ** -0.107804350729586, 30.0], L, 600.0),
+            "C4b_reach50_2x_density_nsims1000": ([1.0, 0.1, 1.0, 50.0], 187.86, 300.0)}
+
+
+def sha256_of(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def golden(name):
+    """a fixture of tests/golden/ written by the sequential CPU mirror (tests/tools/bench_*_cpu.py), or None"""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", name)) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def hash_check(mine, gold, applicable=True):
+    """{key: value of this run} next to the CPU mirror's values of the same keys; match = all equal (None: no fixture)"""
+    out = dict(mine)
+    ok = None
+    if gold is not None and applicable:
+        ok = True
+        for k, v in mine.items():
+            out["cpu_mirror_" + k] = gold.get(k)
+            ok = ok and gold.get(k) == v
+    out["match"] = ok
+    return out
 
 
 def config(world):
@@ -448,6 +486,15 @@ def main():
                 "table_sha256": hashlib.sha256(np.ascontiguousarray(tab3).tobytes()).hexdigest(),
                 "n_used_sha256": hashlib.sha256(np.ascontiguousarray(nu3).tobytes()).hexdigest(),
             }
+            # the same table and stopping indices built by the sequential CPU mirror (tests/tools/strong_table_cpu.py)
+            try:
+                gs = golden("bench_strong_table_sha256.json")
+                strong["parity"] = hash_check(
+                    {"table_sha256": strong["table_sha256"], "n_used_sha256": strong["n_used_sha256"]}, gs,
+                    gs is not None and gs.get("seed") == SEED and tuple(gs.get("lattice", ())) == tuple(C3_LATTICE)
+                    and tuple(gs.get("terminator", ())) == tuple(C3_TERM))
+            except Exception as e:                       # never let the check cost the bench line
+                strong["parity"] = {"error": repr(e)}
             c3 = {
                 "what": "paper-scale build (42x40x30x30 = 1,512,000 points, VarianceTerminator(0.01,15,250)) projected from "
                         "the lattice above: seconds x %d/%d" % (PF, P3),
@@ -456,22 +503,32 @@ def main():
         # small-batch regime (BASELINE configs 0 and 3 with the reference's nsims = 1000)
         if rank == 0:
             small = {}
-            cases = {"C1_default_reach30_25nM_nsims1000": ([10 ** -2.8789331867029184, 10 ** -1.3886105070021626,
-                                                            10 ** -0.107804350729586, 30.0], L, 600.0),
-                     "C4b_reach50_2x_density_nsims1000": ([1.0, 0.1, 1.0, 50.0], 187.86, 300.0)}
-            for nm, (pt, Lc, ts) in cases.items():
-                simc = sprb200.SimSpec(NPART, DIM, Lc, ts, 150.0, np.arange(0.0, ts + 0.5, 1.0))
-                eng.simulate(simc, [pt], _lib.make_run(nsims=1000, seed=SEED), want=("mean",))
+            gold_small = golden("bench_small_batch_sha256.json")
+            for nm, (pt, Lc, ts) in small_batch_cases(L).items():
+                simc = sprb200.SimSpec(NPART, DIM, Lc, ts, SMALL_TOFF, np.arange(0.0, ts + 0.5, 1.0))
+                warm = eng.simulate(simc, [pt], _lib.make_run(nsims=SMALL_NSIMS, seed=SEED), want=("mean", "sum", "n_events"))
                 best = None
                 for rep in range(3):
                     t1 = time.perf_counter()
-                    eng.simulate(simc, [pt], _lib.make_run(nsims=1000, seed=SEED + 1 + rep), want=("mean",))
+                    eng.simulate(simc, [pt], _lib.make_run(nsims=SMALL_NSIMS, seed=SEED + 1 + rep), want=("mean",))
                     wall = time.perf_counter() - t1
                     st = eng.stats()
                     if best is None or wall < best[0]:
                         best = (wall, st)
                 small[nm] = {"wall_ms": best[0] * 1e3, "device_ms": best[1]["device_ms"], "events": best[1]["events"],
                              "events_per_sec": best[1]["events"] / best[0]}
+                # bit-exact parity of the untimed warm call (seed SEED): integer sums over the 1000 replicates and the
+                # event count against the sequential CPU mirror (tests/tools/bench_small_cpu.py)
+                try:
+                    small[nm]["parity"] = hash_check(
+                        {"sum_sha256": sha256_of(warm["sum"]), "events": int(warm["n_events"][0])},
+                        (gold_small or {}).get(nm), gold_small is not None and gold_small.get("seed") == SEED
+                        and gold_small.get("nsims") == SMALL_NSIMS)
+                    if small[nm]["parity"]["match"] is not None:     # the timed seeds: event counts only
+                        small[nm]["parity"]["timed_events_match"] = \
+                            int(best[1]["events"]) in gold_small[nm].get("events_of_timed_seeds", [])
+                except Exception as e:                   # never let the check cost the bench line
+                    small[nm]["parity"] = {"error": repr(e)}
 
     if rank == 0:
         # ---- roofline of the dominant kernel (spr_traj_kernel): SM issue rate and shared-memory bandwidth

@@ -241,3 +241,31 @@ def test_bench_parity_fixture_matches_the_bench_workload():
     for k, v in gold.items():
         if k.isdigit():
             assert v["points"] == gold["1"]["points"] * int(k) and len(v["table_sha256"]) == 64
+
+
+def test_bench_secondary_parity_fixtures(built_lib, oracle_libs):
+    """bench.py's `strong` and `small_batch` blocks compare their hashes with tests/golden/bench_strong_table_sha256.json
+    and bench_small_batch_sha256.json (sequential CPU mirror): the fixtures must describe the workloads bench.py runs,
+    and the cheap one (C1, 1000 replicates: 2 s) is rebuilt here"""
+    import importlib.util
+    import json
+    from oracle import mirror_oracle as M
+    from sprb200 import _lib
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    B = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(B)
+    gs = B.golden("bench_strong_table_sha256.json")
+    assert gs["seed"] == B.SEED and tuple(gs["lattice"]) == B.C3_LATTICE and tuple(gs["terminator"]) == B.C3_TERM
+    assert gs["points"] == int(np.prod(B.C3_LATTICE)) and len(gs["table_sha256"]) == 64 and len(gs["n_used_sha256"]) == 64
+    gb = B.golden("bench_small_batch_sha256.json")
+    assert gb["seed"] == B.SEED and gb["nsims"] == B.SMALL_NSIMS
+    cases = B.small_batch_cases(_lib.domain_length(B.NPART, B.DIM))
+    assert set(cases) <= set(gb)
+    nm = "C1_default_reach30_25nM_nsims1000"
+    pt, Lc, ts = cases[nm]
+    sm = M.Sim(N=B.NPART, DIM=B.DIM, L=Lc, tstop=ts, tstop_AtoB=B.SMALL_TOFF, tsave=np.arange(0.0, ts + 0.5, 1.0))
+    o = M.point(sm, *pt, B.SEED, 0, nsims=B.SMALL_NSIMS)
+    mine = {"sum_sha256": B.sha256_of(o["sum"].reshape(1, -1)), "events": int(o["n_events"])}
+    chk = B.hash_check(mine, gb[nm])
+    assert chk["match"] is True and chk["cpu_mirror_events"] == mine["events"]
+    assert B.hash_check(mine, None)["match"] is None and B.hash_check({"events": 1}, gb[nm])["match"] is False
