@@ -25,9 +25,9 @@ using SPRFittingPaper2023
 using SPRFittingPaper2023: BioPhysParams, SimParams, SurrogateParams, TotalBoundOutputter,
     TotalAOutputter, SimNumberTerminator, VarianceTerminator, getdim
 import SPRFittingPaper2023: isnotdone, update!, reset!
-using OnlineStats: Variance, Mean, nobs, merge!
+using OnlineStats: Variance, Mean, nobs      # merge! is Base.merge!, which OnlineStatsBase extends
 using StaticArrays: SVector
-using Random: rand, RandomDevice
+using Random: RandomDevice
 
 const LIB = get(ENV, "SPRB200_LIB",
                 joinpath(@__DIR__, "..", "lib", "libsprb200.so"))
