@@ -275,8 +275,10 @@ class ClockSampler:
 def reference_arm(args, K, W):
     """the reference's CPU implementation on the box's host cores; never touches the product or the GPU"""
     cpu = CpuPort()
-    pts = grid_points_np(RANGES, NK + (NREACH_PER_GPU,))
+    world = max(1, args.gpus)                    # the workload of the N-GPU arm: 10 reach values per GPU
+    pts = grid_points_np(RANGES, NK + (NREACH_PER_GPU * world,))
     ev, deg = apriori_events(pts)
+    what = "%d C2 grid" % len(pts)
     for w in range(W):
         cpu.rate(pts, ev, deg, 900 + w, 1000 + w, budget_core_s=4.0 * cpu.ncores)
     vals, secs, rs = [], 0.0, []
@@ -284,7 +286,7 @@ def reference_arm(args, K, W):
         r = cpu.rate(pts, ev, deg, 777 + k, 2000 + k)
         vals.append(r["value"]); secs += r["sample_wall"]; rs.append(r)
     val = float(np.mean(vals))
-    cfg = config(1)
+    cfg = config(world)
     cfg["reference_sample_points_per_step"] = rs[0]["sample_points"]
     cfg["reference_sample_events_per_step"] = rs[0]["sample_events"]
     print(json.dumps({
@@ -294,7 +296,7 @@ def reference_arm(args, K, W):
         "per_step_values": vals, "spread": float((max(vals) - min(vals)) / val),
         "projected_c2_build_seconds": float(np.mean([r["wall_projected"] for r in rs])),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cpu.ncores, "kind": "port",
-                         "sample": sample_text(rs[0], "10^4 C2 grid")},
+                         "sample": sample_text(rs[0], what)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
     return 0

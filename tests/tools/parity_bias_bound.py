@@ -16,7 +16,12 @@ from oracle import mirror_oracle as M, ref_oracle as R
 import test_gpu_parity as tp
 
 nrep = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
-names = sys.argv[2:] or list(tp.CASES)
+# the TotalAOutputter case of tests/test_gpu_parity.py::test_gpu_total_A_observable (A = N - B - 2C, callbacks.jl:111):
+# together with the bound-antibody curve B + C it pins B and C separately
+EXTRA = {"TotalA-observable": (0.05, 0.03, 0.6, 28.0, 500, 3, None, 200.0, 80.0, np.arange(0.0, 201.0, 2.0), 0)}
+OBS = {"TotalA-observable": 1}
+ALL = dict(tp.CASES, **EXTRA)
+names = sys.argv[2:] or list(ALL)
 NT = os.cpu_count() or 1
 CHUNKS = 32
 per = -(-nrep // CHUNKS)
@@ -29,22 +34,22 @@ def pooled(means, variances, n):
     return m, ss / (n * len(means) - 1)
 
 
-def mirror_side(case, seed):
+def mirror_side(case, seed, obs=0):
     kon, koff, konb, reach, N, DIM, L, tstop, toff, tsave, _ = case
     def part(c):
         sm = M.Sim(N=N, DIM=DIM, L=L, tstop=tstop, tstop_AtoB=toff, tsave=tsave)
-        p = M.point(sm, kon, koff, konb, reach, seed, 1000 + c, nsims=per)
+        p = M.point(sm, kon, koff, konb, reach, seed, 1000 + c, nsims=per, observable=obs)
         s, q, n = p["sum"].astype(np.float64), p["sumsq"].astype(np.float64), p["n_used"]
         return s / n / N, (q - s * s / n) / (n - 1) / N ** 2, p["n_events"] / n
     with ThreadPoolExecutor(NT) as ex:
         return list(ex.map(part, range(CHUNKS)))
 
 
-def oracle_side(case, seed):
+def oracle_side(case, seed, obs=0):
     kon, koff, konb, reach, N, DIM, L, tstop, toff, tsave, _ = case
     sim = R.make_sim(N=N, DIM=DIM, tstop=tstop, tstop_AtoB=toff, tsave=tsave, L=L, nsims=per)
     def part(c):
-        r = R.run(kon, koff, konb, reach, sim, seed=seed, stream=1000 + c)
+        r = R.run(kon, koff, konb, reach, sim, seed=seed, stream=1000 + c, observable=obs)
         return r["mean"], r["var"], r["nevents"] / per
     with ThreadPoolExecutor(NT) as ex:
         return list(ex.map(part, range(CHUNKS)))
@@ -61,13 +66,14 @@ def scalar(gs, rs):
 print("# mirror (== GPU bit for bit) vs reference-algorithm oracle: %d chunks x %d replicates per side, %d host threads"
       % (CHUNKS, per, NT))
 for name in names:
-    case = list(tp.CASES[name])
+    case = list(ALL[name])
+    obs = OBS.get(name, 0)
     N, DIM = case[4], case[5]
     case[6] = R.default_L(N, DIM) if case[6] is None else case[6]
     t0 = time.time()
-    g = mirror_side(case, 424242)
+    g = mirror_side(case, 424242, obs)
     t1 = time.time()
-    r = oracle_side(case, 171717)
+    r = oracle_side(case, 171717, obs)
     t2 = time.time()
     gm, gv = pooled([c[0] for c in g], [c[1] for c in g], per)
     rm, rv = pooled([c[0] for c in r], [c[1] for c in r], per)
