@@ -426,7 +426,7 @@ def main():
     def e2e_step(seed):
         run = _lib.make_run(nsims=NREP, seed=seed)
         tab, nu, nev = eng.build_table_dist(grid, sim, run, host=(rank == 0), want_counts=(rank == 0))
-        last["table"] = tab
+        last["table"], last["nev"] = tab, nev
         return eng.stats()["events"]
 
     e2e_step(SEED + E2E_WARM_SEED_OFFSET)
@@ -444,6 +444,10 @@ def main():
             if gold.get("seed") == parity["seed"] and gold.get("replicates") == NREP and str(world) in gold:
                 parity["cpu_mirror_sha256"] = gold[str(world)]["table_sha256"]
                 parity["match"] = parity["cpu_mirror_sha256"] == parity["table_sha256"]
+                # the SSA events of the same build, summed over all points (per-point counters gathered by the call)
+                parity["events"] = int(np.asarray(last["nev"], dtype=np.uint64).sum())
+                parity["cpu_mirror_events"] = gold[str(world)].get("events")
+                parity["events_match"] = parity["events"] == parity["cpu_mirror_events"]
         except Exception as e:                       # never let the check cost the bench line
             parity = {"error": repr(e)} if parity is None else dict(parity, error=repr(e))
     barrier()
