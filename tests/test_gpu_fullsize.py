@@ -1,7 +1,9 @@
 """-m gpu: BASELINE.json's full-size configurations through size-independent properties (the oracle cannot
 finish these in seconds): reproducibility under re-batching, range and monotonicity of the table, particle
-conservation of raw curves in the dense stress case."""
+conservation of raw curves in the dense stress case -- and, for config 2, the sha256 of the complete result against
+the one the sequential CPU mirror produced beforehand (tests/golden/c2_full_rows_sha256.json)."""
 import hashlib
+import json
 import os
 
 import numpy as np
@@ -23,6 +25,14 @@ def test_c2_full_grid_is_batching_independent_and_physical(engine):
     idx = np.arange(1, 10001)
     rows, nu, nev = engine.build_indices(grid, sim, run, idx)
     assert engine.stats()["trajectories"] == 1000000 and int(nev.sum()) == engine.stats()["events"]
+    # bit-exact parity at full size: the same 10^4 mean curves and per-point event counts (8.3e9 events) built by the
+    # sequential CPU mirror oracle/spr_mirror.c, which shares no code with the kernels (tests/tools/c2_table_cpu.py)
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c2_full_rows_sha256.json")) as f:
+        gold = json.load(f)
+    assert gold["seed"] == 20231 and gold["replicates"] == 100 and gold["points"] == len(idx)
+    assert int(nev.sum()) == gold["events"]
+    assert hashlib.sha256(np.ascontiguousarray(nev).tobytes()).hexdigest() == gold["n_events_sha256"]
+    assert hashlib.sha256(np.ascontiguousarray(rows).tobytes()).hexdigest() == gold["rows_sha256"]
     os.environ["SPRB200_CURVE_BYTES"] = str(320 << 20)
     os.environ["SPRB200_TABLE_BYTES"] = str(2 << 30)
     try:
@@ -66,3 +76,10 @@ def test_c4_dense_stress_conserves_particles(engine):
     assert int(nev[0]) > 64 * 50000
     out = engine.simulate(sim, [[1.0, 0.1, 1.0, 50.0]], sprb200.make_run(nsims=64, seed=4))
     assert np.array_equal(out["sum"][0], bound.sum(axis=0))
+    # bit-exact against the sequential CPU mirror (tests/tools/c4_sums_cpu.py): sums, sums of squares, event count
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c4b_sums_sha256.json")) as f:
+        gold = json.load(f)
+    assert gold["seed"] == 4 and gold["replicates"] == 64 and abs(gold["L"] - L2) < 1e-12
+    assert int(nev[0]) == gold["events"] and int(out["n_events"][0]) == gold["events"]
+    assert hashlib.sha256(np.ascontiguousarray(out["sum"][0]).tobytes()).hexdigest() == gold["sum_sha256"]
+    assert hashlib.sha256(np.ascontiguousarray(out["sumsq"][0]).tobytes()).hexdigest() == gold["sumsq_sha256"]
